@@ -1,0 +1,226 @@
+"""Pins the CPU oracle to the reference's own golden vectors.
+
+CPU only.  Every byte-level pin the reference holds for the lossless encode path is
+checked here before the oracle is trusted as the checker for the CUDA path."""
+import struct
+
+import numpy as np
+import pytest
+
+from helpers import (LOSSLESS_EXAMPLES, coded_channels_of_frame, file_to_f32_input, golden_audio_wav_f32,
+                     golden_bytes, oracle, pcm16_to_f32, synth_pcm16)
+
+
+# ---- G3: CRC32 known answers (libflo/tests/rust/core_crc32_tests.rs:5-14) ----
+def test_crc32_known_answers():
+    assert oracle.crc32(b"") == 0
+    assert oracle.crc32(b"123456789") == 0xCBF43926
+
+
+def test_crc32_matches_zlib():
+    import zlib
+    rng = np.random.default_rng(1)
+    for n in (1, 2, 3, 255, 4096, 100001):
+        b = rng.integers(0, 256, n, dtype=np.uint8).tobytes()
+        assert oracle.crc32(b) == zlib.crc32(b)
+
+
+# ---- G4: Rice vectors (libflo/tests/rust/core_rice_tests.rs:19-58) ----
+def test_rice_roundtrip_i32_reference_vector():
+    r = [100, -200, 50, -10, 0, 150, -300]
+    k = oracle.estimate_rice_parameter_i32(r)
+    enc = oracle.rice_encode_i32(r, k)
+    assert oracle.rice_decode_i32(enc, k, len(r)).tolist() == r
+    # closed form of rice.rs:29-69: max_abs=300 -> 2*300=600 -> 10 bits -> min_k=2; mean=115 -> mean_k=7
+    assert k == 7
+
+
+def test_rice_bit_order_msb_first():
+    # k=0: value u is u ones then a zero.  [1, -1] -> u = 2, 1 -> bits 110 10 -> 0b11010_000
+    assert oracle.rice_encode_i32([1, -1], 0) == bytes([0b11010000])
+    # k=3: r=5 -> u=10 -> q=1, rem=2 -> 1 0 010 ; r=-3 -> u=5 -> q=0 rem=5 -> 0 101
+    assert oracle.rice_encode_i32([5, -3], 3) == bytes([0b10010010, 0b10000000])
+
+
+def test_rice_zigzag_and_cap():
+    for v in (0, 1, -1, 2, -2, 100, -100):
+        enc = oracle.rice_encode_i32([v], 4)
+        assert oracle.rice_decode_i32(enc, 4, 1).tolist() == [v]
+    # quotient capped at 255 ones (rice.rs:103-108)
+    enc = oracle.rice_encode_i32([10000], 0)
+    assert len(enc) == 32 and enc == bytes([0xFF] * 31 + [0xFE])
+
+
+def test_rice_parameter_rules():
+    assert oracle.estimate_rice_parameter_i32([]) == 4
+    assert oracle.estimate_rice_parameter_i32([0, 0, 0]) == 0
+    small = oracle.estimate_rice_parameter_i32([0, 1, -1, 2, -2, 1, 0, -1])
+    large = oracle.estimate_rice_parameter_i32([1000, -2000, 1500, -1800, 2200])
+    assert large > small                       # lossless_lpc_tests.rs:122-133
+    assert oracle.estimate_rice_parameter_i32([2 ** 30]) == 15   # clamp
+
+
+# ---- G5: fixed predictor vectors (lossless_lpc_tests.rs:102-120) ----
+def test_fixed_predictor_vectors():
+    s = [100, 200, 300, 400, 500]
+    assert oracle.fixed_predictor_residuals(s, 0).tolist() == s
+    assert oracle.fixed_predictor_residuals(s, 1).tolist() == [100, 100, 100, 100, 100]
+    assert oracle.fixed_predictor_residuals(s, 2).tolist() == [100, 100, 0, 0, 0]
+    assert oracle.fixed_predictor_residuals(s, 3).tolist() == [100, 100, 0, 0, 0]
+    assert oracle.fixed_predictor_residuals(s, 4).tolist() == [100, 100, 0, 0, 0]
+    assert oracle.fixed_predictor_residuals([7], 4).tolist() == [7]
+
+
+def test_autocorr_int_properties():
+    s = [(i * 100) % 32767 for i in range(100)]       # lossless_lpc_tests.rs:91-100
+    ac = oracle.autocorr_int(s, 4)
+    assert len(ac) == 5
+    assert all(ac[0] >= abs(ac[i]) for i in range(1, 5))
+    a = np.array(s, dtype=np.int64)
+    for lag in range(5):
+        assert ac[lag] == int(np.dot(a[lag:], a[:len(a) - lag]))
+
+
+def test_f32_to_i32_rules():
+    f = oracle.f32_to_i32
+    assert f(0.0) == 0 and f(1.0) == 32767 and f(-1.0) == -32767
+    assert f(2.0) == 32767 and f(-2.0) == -32768
+    assert f(float("nan")) == 0 and f(float("inf")) == 32767 and f(float("-inf")) == -32768
+    assert f(0.99999) == 32766 and f(-0.5) == -16383     # truncation toward zero
+    # PCM16 -> f32 (1/32768) -> *32767 shrinks every non-zero sample by one LSB
+    for s, v in ((1, 0), (-1, 0), (32767, 32766), (-32768, -32767), (1000, 999)):
+        assert f(float(np.float32(s) * np.float32(1 / 32768))) == v
+
+
+# ---- G2: fixed-point re-encode of every shipped lossless example ----
+@pytest.mark.parametrize("name", LOSSLESS_EXAMPLES)
+def test_examples_frames_reencode_bit_exact(name):
+    f = oracle.FloFile(golden_bytes(name))
+    assert f.level == 5
+    assert oracle.crc32(f.data_chunk()) == f.crc32
+    for i, fr in enumerate(f.frames):
+        orig = f.frame_bytes(i)
+        if fr.frame_type == 0:
+            assert orig == bytes([0]) + struct.pack("<I", fr.frame_samples) + bytes([0]) + bytes(4 * f.channels)
+            continue
+        chans = coded_channels_of_frame(f, i)
+        assert oracle.encode_frame_i32(chans, fr.frame_samples, fr.flags, f.level) == orig, (name, i)
+
+
+@pytest.mark.parametrize("name", LOSSLESS_EXAMPLES)
+def test_examples_whole_file_from_f32(name):
+    """Encoder::encode on f32 input reproduces the whole reference file (header, TOC, DATA,
+    CRC, metadata tail passed through verbatim)."""
+    gold = golden_bytes(name)
+    f = oracle.FloFile(gold)
+    x = file_to_f32_input(f)
+    meta = gold[len(gold) - f.meta_size:] if f.meta_size else b""
+    out = oracle.encode(x, f.sample_rate, f.channels, f.bit_depth, f.level, meta)
+    assert out == gold
+
+
+def test_telephone_is_lpc5():
+    f = oracle.FloFile(golden_bytes("telephone_8khz.flo"))
+    ch = f.frames[0].channels[0]
+    assert (ch.n_coeffs, ch.shift_bits, ch.k) == (5, 15, 8)
+    assert ch.coeffs[:3] == [51426, -41731, 8660]
+
+
+# ---- G1: Examples/audio.wav -> audio_lossless.flo ----
+def test_audio_wav_config1():
+    x, sr, ch = golden_audio_wav_f32()
+    assert (sr, ch, x.size) == (44100, 2, 88200) and not x.any()
+    gold = golden_bytes("audio_lossless.flo")
+    out = oracle.encode(x, sr, ch, 16, 5, b"")
+    # bytes [0,62) = magic+header up to meta_size; [62,70) = meta_size (0 here, 138 in the shipped file);
+    # [70,108) = TOC + DATA (one Silence frame)
+    assert len(out) == 108 and out[:62] == gold[:62] and out[70:108] == gold[70:108]
+    assert struct.unpack_from("<Q", gold, 62)[0] == 138
+    # with the reference's own metadata bytes the whole 246-byte file matches
+    assert oracle.encode(x, sr, ch, 16, 5, gold[108:]) == gold
+
+
+# ---- G6: container properties (integration_tests.rs:49-67, edge_case_tests.rs:77-116) ----
+def test_container_three_seconds_48k_stereo():
+    pcm = synth_pcm16(144000, 2, 48000, seed=3)
+    out = oracle.encode(pcm16_to_f32(pcm), 48000, 2, 16, 5, b"")
+    f = oracle.FloFile(out)
+    assert f.total_samples == 144000 and f.num_frames == 3
+    assert oracle.crc32(f.data_chunk()) == f.crc32
+    assert [fr.timestamp_ms for fr in f.frames] == [0, 1000, 2000]
+    off = 0
+    for fr in f.frames:
+        assert fr.byte_offset == off
+        off += fr.frame_size
+    assert off == f.data_size
+
+
+@pytest.mark.parametrize("n", [1, 2, 44099, 44100, 44101, 88200, 88201])
+def test_frame_boundary_lengths_roundtrip(n):
+    pcm = synth_pcm16(n, 1, 44100, seed=n)
+    x = pcm16_to_f32(pcm)
+    out = oracle.encode(x, 44100, 1, 16, 5, b"")
+    f = oracle.FloFile(out)
+    assert f.total_samples == n and f.num_frames == -(-n // 44100)
+    want = np.array([oracle.f32_to_i32(float(v)) for v in x[:2000]], dtype=np.int32)
+    got = oracle.decode_i32(out)
+    assert got.size == n
+    # Reference quirk (encoder.rs:115-119 + writer.rs:267-270): when fixed order 0 wins in every channel the
+    # frame is typed Raw and only the Rice bytes survive, so the reference's own decoder cannot recover the
+    # samples.  Sample equality is only asserted for frames that are not of that kind.
+    quirk = any(fr.frame_type == 254 and fr.channels[0].residual_bytes != 2 * fr.frame_samples for fr in f.frames)
+    assert not quirk or n % 44100 in (1, 2)
+    if n > 2:
+        assert np.array_equal(got[:want.size], want)
+
+
+@pytest.mark.parametrize("level", range(10))
+def test_all_levels_roundtrip_stereo_midside(level):
+    """Consistency (not a pin): every level decodes back to the quantised input, with mid/side on."""
+    n = 6000
+    pcm = synth_pcm16(n, 2, 8000, seed=level)
+    x = pcm16_to_f32(pcm)
+    out = oracle.encode(x, 8000, 2, 16, level, b"meta")
+    f = oracle.FloFile(out)
+    assert f.level == level and out.endswith(b"meta")
+    assert any(fr.flags & 1 for fr in f.frames)          # correlated channels -> mid/side chosen
+    want = (x.astype(np.float32) * np.float32(32767.0)).clip(-32768, 32767).astype(np.int32)
+    if level > 0:
+        assert np.array_equal(oracle.decode_i32(out), want)
+    else:
+        # level 0 only tries raw + fixed-0, so best_order is always 0 and every frame is typed Raw even
+        # when it holds Rice bytes (the reference cannot decode its own level-0 output; reproduced, not fixed)
+        assert all(fr.frame_type == 254 for fr in f.frames)
+    want_order = {0: 0, 1: 2, 2: 4, 3: 4, 4: 6, 5: 8, 6: 8, 7: 10, 8: 12, 9: 12}[level]
+    for fr in f.frames:
+        assert fr.frame_type in (254, want_order if 1 <= want_order <= 12 else 8)
+
+
+def test_six_channels_and_odd_interleave():
+    pcm = synth_pcm16(3000, 6, 8000, seed=9)
+    x = pcm16_to_f32(pcm)
+    out = oracle.encode(x, 8000, 6, 16, 5, b"")
+    f = oracle.FloFile(out)
+    assert f.channels == 6 and f.total_samples == 3000
+    # odd interleaved length on stereo: trailing element belongs to the (short) last frame
+    x2 = pcm16_to_f32(synth_pcm16(1001, 2, 8000, seed=5))[:2001]
+    out2 = oracle.encode(x2, 8000, 2, 16, 5, b"")
+    f2 = oracle.FloFile(out2)
+    assert f2.total_samples == 1000 and f2.num_frames == 1
+
+
+def test_reference_panics_are_errors():
+    with pytest.raises(RuntimeError):
+        oracle.encode(np.zeros(4, np.float32), 44100, 0)
+    with pytest.raises(RuntimeError):
+        oracle.encode(np.zeros(4, np.float32), 0, 1)
+
+
+def test_empty_and_nan_inputs():
+    out = oracle.encode(np.zeros(0, np.float32), 44100, 2, 16, 5, b"")
+    f = oracle.FloFile(out)
+    assert f.num_frames == 0 and f.total_samples == 0 and len(out) == 70 + 4
+    x = np.array([np.nan, np.inf, -np.inf, 0.25] * 50, np.float32)
+    out = oracle.encode(x, 100, 1, 16, 5, b"")
+    got = oracle.decode_i32(out)
+    assert got[:4].tolist() == [0, 32767, -32768, 8191]
