@@ -1,0 +1,9 @@
+"""flo_b200 -- B200-native (sm_100a) implementation of flo's lossless ALPC encode path.
+
+Drop-in for `libflo_audio::Encoder::{new, with_compression, encode}` only; see DESIGN.md.
+"""
+from ._lib import FMT_F32, FMT_PCM16, FloError, SO_PATH
+from .encoder import Context, Encoder, TrackSpec, default_context, encode_batch
+
+__all__ = ["Encoder", "Context", "TrackSpec", "encode_batch", "default_context", "FloError", "FMT_F32", "FMT_PCM16",
+           "SO_PATH"]

@@ -1,0 +1,468 @@
+// flo_api.cu -- host side of the C ABI declared in include/flo_b200.h.
+//
+// Mirrors the reference's Encoder (libflo/src/lossless/encoder.rs:9-45): a pure
+// function (samples, sample_rate, channels, bit_depth, level, metadata) -> bytes.
+// All arithmetic of the path runs in the kernels of flo_kernels.cu; this file only
+// lays the batch out (frame table, offsets that do not depend on the data), moves
+// buffers and launches.  There is no CPU implementation of any stage here.
+#include <algorithm>
+#include <cstdarg>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <mutex>
+#include <vector>
+
+#include "flo_internal.h"
+
+using namespace flo;
+
+static thread_local char g_err[512] = "";
+static void set_err(const char *fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof g_err, fmt, ap);
+    va_end(ap);
+}
+extern "C" const char *flo_last_error(void) { return g_err; }
+extern "C" const char *flo_version(void) { return "flo_b200 0.1 (sm_100a)"; }
+extern "C" void flo_free(void *p) { free(p); }
+
+#define CK(expr)                                                                           \
+    do {                                                                                   \
+        cudaError_t e_ = (expr);                                                           \
+        if (e_ != cudaSuccess) {                                                           \
+            set_err("CUDA error %s at %s:%d: %s", cudaGetErrorName(e_), __FILE__, __LINE__, \
+                    cudaGetErrorString(e_));                                               \
+            return e_ == cudaErrorMemoryAllocation ? FLO_ERR_NOMEM : FLO_ERR_CUDA;         \
+        }                                                                                  \
+    } while (0)
+
+extern "C" int flo_device_count(void) {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
+    return n;
+}
+
+extern "C" void *flo_host_alloc(size_t bytes) {
+    void *p = nullptr;
+    if (cudaMallocHost(&p, bytes ? bytes : 1) != cudaSuccess) { cudaGetLastError(); return nullptr; }
+    return p;
+}
+extern "C" void flo_host_free(void *p) { if (p) cudaFreeHost(p); }
+
+namespace {
+
+struct DevBuf {                       // grow-only device arena
+    void *p = nullptr;
+    size_t cap = 0;
+    int reserve(size_t bytes) {
+        if (bytes <= cap) return FLO_OK;
+        if (p) cudaFree(p);
+        p = nullptr; cap = 0;
+        size_t want = bytes + bytes / 8 + 256;
+        cudaError_t e = cudaMalloc(&p, want);
+        if (e != cudaSuccess) {
+            cudaGetLastError();
+            e = cudaMalloc(&p, bytes);
+            want = bytes;
+        }
+        if (e != cudaSuccess) { set_err("cudaMalloc(%zu) failed: %s", bytes, cudaGetErrorString(e)); p = nullptr; return FLO_ERR_NOMEM; }
+        cap = want;
+        return FLO_OK;
+    }
+    void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
+};
+
+struct HostBuf {                      // grow-only pinned host arena
+    void *p = nullptr;
+    size_t cap = 0;
+    int reserve(size_t bytes) {
+        if (bytes <= cap) return FLO_OK;
+        if (p) cudaFreeHost(p);
+        p = nullptr; cap = 0;
+        if (cudaMallocHost(&p, bytes + bytes / 8 + 256) != cudaSuccess) { cudaGetLastError(); set_err("cudaMallocHost(%zu) failed", bytes); p = nullptr; return FLO_ERR_NOMEM; }
+        cap = bytes + bytes / 8 + 256;
+        return FLO_OK;
+    }
+    void release() { if (p) cudaFreeHost(p); p = nullptr; cap = 0; }
+};
+
+inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+
+}  // namespace
+
+struct flo_ctx {
+    int device = 0;
+    int sm_count = 0;
+    size_t smem_optin = 0;
+    std::mutex mu;
+    cudaStream_t own_stream = nullptr, stream = nullptr;
+    cudaEvent_t ev[8] = {};
+    DevBuf in, out, meta, tracks, frames, ctrl, fexcl, fsize, segcrc, foff, plane, cres, report;
+    HostBuf h_small, h_out;
+    bool report_on = false;
+    uint32_t report_frames = 0;
+    float ms[6] = {0, 0, 0, 0, 0, 0};
+    uint32_t launches = 0;
+};
+
+extern "C" int flo_ctx_create(int device, flo_ctx **out) {
+    if (!out) { set_err("flo_ctx_create: out is NULL"); return FLO_ERR_ARG; }
+    *out = nullptr;
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess || n == 0) {
+        cudaGetLastError();
+        set_err("no CUDA device available (%s); flo_b200 has no CPU fallback", e == cudaSuccess ? "device count 0" : cudaGetErrorString(e));
+        return FLO_ERR_CUDA;
+    }
+    if (device < 0 || device >= n) { set_err("device %d out of range (0..%d)", device, n - 1); return FLO_ERR_ARG; }
+    CK(cudaSetDevice(device));
+    cudaDeviceProp prop;
+    CK(cudaGetDeviceProperties(&prop, device));
+    if (prop.major < 10) { set_err("device %d is sm_%d%d; this library is built for sm_100a only", device, prop.major, prop.minor); return FLO_ERR_CUDA; }
+    flo_ctx *c = new (std::nothrow) flo_ctx();
+    if (!c) { set_err("out of host memory"); return FLO_ERR_NOMEM; }
+    c->device = device;
+    c->sm_count = prop.multiProcessorCount;
+    c->smem_optin = prop.sharedMemPerBlockOptin;
+    cudaError_t e2 = cudaStreamCreateWithFlags(&c->own_stream, cudaStreamNonBlocking);
+    if (e2 != cudaSuccess) { set_err("cudaStreamCreate: %s", cudaGetErrorString(e2)); delete c; return FLO_ERR_CUDA; }
+    c->stream = c->own_stream;
+    for (auto &ev : c->ev) cudaEventCreate(&ev);
+    upload_crc_tables();
+    e2 = configure_encode_kernel(c->smem_optin);
+    if (e2 != cudaSuccess) { set_err("cudaFuncSetAttribute(max dynamic smem %zu): %s", c->smem_optin, cudaGetErrorString(e2)); flo_ctx_destroy(c); return FLO_ERR_CUDA; }
+    e2 = cudaDeviceSynchronize();
+    if (e2 != cudaSuccess) { set_err("device init: %s", cudaGetErrorString(e2)); flo_ctx_destroy(c); return FLO_ERR_CUDA; }
+    *out = c;
+    return FLO_OK;
+}
+
+extern "C" void flo_ctx_destroy(flo_ctx *c) {
+    if (!c) return;
+    cudaSetDevice(c->device);
+    cudaDeviceSynchronize();
+    for (DevBuf *b : {&c->in, &c->out, &c->meta, &c->tracks, &c->frames, &c->ctrl, &c->fexcl, &c->fsize, &c->segcrc,
+                      &c->foff, &c->plane, &c->cres, &c->report})
+        b->release();
+    c->h_small.release();
+    c->h_out.release();
+    for (auto &ev : c->ev) if (ev) cudaEventDestroy(ev);
+    if (c->own_stream) cudaStreamDestroy(c->own_stream);
+    delete c;
+}
+
+extern "C" int flo_ctx_set_stream(flo_ctx *c, void *cuda_stream) {
+    if (!c) { set_err("ctx is NULL"); return FLO_ERR_ARG; }
+    std::lock_guard<std::mutex> lk(c->mu);
+    c->stream = cuda_stream ? (cudaStream_t)cuda_stream : c->own_stream;
+    return FLO_OK;
+}
+
+extern "C" int flo_ctx_last_timing(flo_ctx *c, float ms[6], uint32_t *launches) {
+    if (!c) { set_err("ctx is NULL"); return FLO_ERR_ARG; }
+    std::lock_guard<std::mutex> lk(c->mu);
+    if (ms) memcpy(ms, c->ms, sizeof c->ms);
+    if (launches) *launches = c->launches;
+    return FLO_OK;
+}
+
+extern "C" int flo_ctx_enable_report(flo_ctx *c, int enable) {
+    if (!c) { set_err("ctx is NULL"); return FLO_ERR_ARG; }
+    std::lock_guard<std::mutex> lk(c->mu);
+    c->report_on = enable != 0;
+    return FLO_OK;
+}
+
+extern "C" int flo_ctx_read_report(flo_ctx *c, uint32_t frame, uint32_t channel, flo_cand_report out[14]) {
+    if (!c || !out) { set_err("bad argument"); return FLO_ERR_ARG; }
+    std::lock_guard<std::mutex> lk(c->mu);
+    if (!c->report.p || frame >= c->report_frames || channel >= (uint32_t)REPORT_CH) { set_err("no report for frame %u channel %u", frame, channel); return FLO_ERR_ARG; }
+    CK(cudaSetDevice(c->device));
+    const flo_cand_report *src = (const flo_cand_report *)c->report.p + ((size_t)frame * REPORT_CH + channel) * NCAND;
+    CK(cudaMemcpy(out, src, sizeof(flo_cand_report) * NCAND, cudaMemcpyDeviceToHost));
+    return FLO_OK;
+}
+
+// ---- batch layout -----------------------------------------------------------------
+namespace {
+
+struct Layout {
+    std::vector<TrackDev> tr;
+    uint64_t n_frames = 0;
+    uint64_t n_segs = 0;
+    uint64_t out_bound = 0;
+    uint64_t meta_total = 0;
+    uint64_t in_bytes = 0;            // host-input arena bytes
+    std::vector<uint64_t> in_off;     // byte offset of each track in the input arena
+    uint64_t max_plane_elems = 0;     // C * stride of the largest frame
+};
+
+// worst-case bytes of one frame: 6 + C * (4 + 1 + 48 + 3 + 2 n)   (types.rs:242-267, raw payload bound)
+inline uint64_t frame_bound(uint64_t cl0, uint64_t C) { return 6 + C * (4 + 52 + 2 * cl0); }
+
+int make_layout(const flo_track *tracks, size_t n_tracks, int format, Layout &L) {
+    const size_t esz = format == FLO_FMT_PCM16 ? 2 : 4;
+    L.tr.resize(n_tracks);
+    L.in_off.resize(n_tracks);
+    uint64_t stat = 0, frames = 0, segs = 0, bound = 0, meta = 0, inb = 0;
+    for (size_t t = 0; t < n_tracks; t++) {
+        const flo_track &k = tracks[t];
+        if (k.channels == 0) { set_err("track %zu: channels == 0 (the reference panics: division by zero, encoder.rs:48)", t); return FLO_ERR_ARG; }
+        if (k.sample_rate == 0) { set_err("track %zu: sample_rate == 0 (the reference panics: division by zero, encoder.rs:50)", t); return FLO_ERR_ARG; }
+        if (k.n_interleaved && !k.samples) { set_err("track %zu: samples is NULL", t); return FLO_ERR_ARG; }
+        if (k.meta_len && !k.meta) { set_err("track %zu: meta is NULL", t); return FLO_ERR_ARG; }
+        const uint64_t C = k.channels, sr = k.sample_rate;
+        if (sr * C > (1ull << 28)) { set_err("track %zu: sample_rate * channels too large for one frame", t); return FLO_ERR_ARG; }
+        const uint64_t total = k.n_interleaved / C;                   // encoder.rs:48
+        const uint64_t nf = (total + sr - 1) / sr;                    // encoder.rs:50
+        if (frames + nf > 0xFFFFFFF0ull) { set_err("batch has too many frames"); return FLO_ERR_ARG; }
+        TrackDev &d = L.tr[t];
+        memset(&d, 0, sizeof d);
+        d.n_inter = k.n_interleaved;
+        d.static_off = stat;
+        d.meta_off = meta;
+        d.meta_len = k.meta_len;
+        d.sample_rate = k.sample_rate;
+        d.channels = k.channels;
+        d.bit_depth = k.bit_depth;
+        d.first_frame = (uint32_t)frames;
+        d.n_frames = (uint32_t)nf;
+        d.first_seg = (uint32_t)segs;
+        uint64_t dbound = 0;
+        if (nf) {
+            const uint64_t full = frame_bound(sr, C);
+            const uint64_t last_len = k.n_interleaved - (nf - 1) * sr * C;
+            const uint64_t last_cl0 = std::min<uint64_t>((last_len + C - 1) / C, sr + 1);
+            dbound = (nf - 1) * full + frame_bound(last_cl0, C);
+            const uint64_t cl0 = nf > 1 ? sr : last_cl0;
+            const uint64_t stride = (cl0 + 15) & ~15ull;
+            L.max_plane_elems = std::max(L.max_plane_elems, C * stride);
+        }
+        const uint64_t fixed = FILE_HDR + 4 + 20 * nf + k.meta_len;
+        stat += fixed;
+        bound += fixed + dbound;
+        frames += nf;
+        segs += (dbound + CRC_SEG - 1) / CRC_SEG;
+        if (segs > 0xFFFFFFF0ull) { set_err("batch too large"); return FLO_ERR_ARG; }
+        meta += k.meta_len;
+        L.in_off[t] = inb;
+        inb += align_up(k.n_interleaved * esz, 256);
+    }
+    L.n_frames = frames; L.n_segs = segs; L.out_bound = bound + 64; L.meta_total = meta; L.in_bytes = inb;
+    return FLO_OK;
+}
+
+}  // namespace
+
+extern "C" size_t flo_output_bound(const flo_track *tracks, size_t n_tracks) {
+    Layout L;
+    if (make_layout(tracks, n_tracks, FLO_FMT_F32, L) != FLO_OK) return 0;
+    return (size_t)L.out_bound;
+}
+
+// ---- the batch pass ----------------------------------------------------------------
+static int encode_batch_impl(flo_ctx *c, const flo_track *tracks, size_t n_tracks, int format, uint8_t level,
+                             bool host_inputs, void *d_out, size_t d_out_cap, uint64_t *offsets, uint64_t *lens) {
+    if (format != FLO_FMT_F32 && format != FLO_FMT_PCM16) { set_err("unknown sample format %d", format); return FLO_ERR_ARG; }
+    if (n_tracks == 0) return FLO_OK;
+    if (level > 9) level = 9;                                          // with_compression, encoder.rs:26-29
+    CK(cudaSetDevice(c->device));
+    Layout L;
+    int rc = make_layout(tracks, n_tracks, format, L);
+    if (rc) return rc;
+    const size_t esz = format == FLO_FMT_PCM16 ? 2 : 4;
+    cudaStream_t st = c->stream;
+
+    uint8_t *out = (uint8_t *)d_out;
+    if (!out) {
+        if ((rc = c->out.reserve(L.out_bound))) return rc;
+        out = (uint8_t *)c->out.p;
+    } else {
+        if (d_out_cap < L.out_bound) { set_err("d_out_capacity %zu < flo_output_bound %llu", d_out_cap, (unsigned long long)L.out_bound); return FLO_ERR_ARG; }
+        if ((uintptr_t)out & 15) { set_err("d_out must be 16-byte aligned"); return FLO_ERR_ARG; }
+    }
+    const uint32_t NF = (uint32_t)L.n_frames, NSEG = (uint32_t)L.n_segs, NTR = (uint32_t)n_tracks;
+    if ((rc = c->tracks.reserve(sizeof(TrackDev) * n_tracks))) return rc;
+    if ((rc = c->frames.reserve(sizeof(uint2) * std::max<uint64_t>(NF, 1)))) return rc;
+    if ((rc = c->ctrl.reserve(8ull * NF + 64))) return rc;             // status words + ticket + err
+    if ((rc = c->fexcl.reserve(8ull * std::max<uint64_t>(NF, 1)))) return rc;
+    if ((rc = c->fsize.reserve(4ull * std::max<uint64_t>(NF, 1)))) return rc;
+    if ((rc = c->segcrc.reserve(4ull * std::max<uint64_t>(NSEG, 1)))) return rc;
+    if ((rc = c->foff.reserve(16ull * n_tracks))) return rc;
+    if ((rc = c->meta.reserve(std::max<uint64_t>(L.meta_total, 1)))) return rc;
+    if ((rc = c->h_small.reserve(sizeof(TrackDev) * n_tracks + L.meta_total + 16ull * n_tracks + 64))) return rc;
+
+    const size_t smem_static = align_up(encode_static_smem(), 16);
+    const size_t dyn = c->smem_optin;
+    const size_t plane_cap = dyn - smem_static;
+    const int grid = (int)std::min<uint64_t>(std::max<uint64_t>(NF, 1), (uint64_t)c->sm_count);
+    if ((rc = c->cres.reserve(sizeof(ChanResult) * 256ull * grid))) return rc;
+    uint64_t plane_elems = 0;
+    if (L.max_plane_elems * 2 > plane_cap) {
+        plane_elems = align_up(L.max_plane_elems, 64);
+        if ((rc = c->plane.reserve(plane_elems * 2 * grid))) return rc;
+    }
+    if (c->report_on) {
+        if ((rc = c->report.reserve(sizeof(flo_cand_report) * NCAND * REPORT_CH * std::max<uint64_t>(NF, 1)))) return rc;
+        c->report_frames = NF;
+    }
+
+    // inputs
+    CK(cudaEventRecord(c->ev[0], st));
+    if (host_inputs) {
+        if ((rc = c->in.reserve(std::max<uint64_t>(L.in_bytes, 1)))) return rc;
+        for (size_t t = 0; t < n_tracks; t++) {
+            L.tr[t].samples = (const uint8_t *)c->in.p + L.in_off[t];
+            if (tracks[t].n_interleaved)
+                CK(cudaMemcpyAsync((uint8_t *)c->in.p + L.in_off[t], tracks[t].samples, tracks[t].n_interleaved * esz,
+                                   cudaMemcpyHostToDevice, st));
+        }
+    } else {
+        for (size_t t = 0; t < n_tracks; t++) {
+            L.tr[t].samples = tracks[t].samples;
+            if (((uintptr_t)tracks[t].samples & (esz - 1)) != 0) { set_err("track %zu: device samples pointer not aligned to the sample size", t); return FLO_ERR_ARG; }
+        }
+    }
+    // small tables through pinned staging
+    uint8_t *hs = (uint8_t *)c->h_small.p;
+    memcpy(hs, L.tr.data(), sizeof(TrackDev) * n_tracks);
+    uint8_t *hmeta = hs + sizeof(TrackDev) * n_tracks;
+    for (size_t t = 0; t < n_tracks; t++)
+        if (tracks[t].meta_len) memcpy(hmeta + L.tr[t].meta_off, tracks[t].meta, tracks[t].meta_len);
+    CK(cudaMemcpyAsync(c->tracks.p, hs, sizeof(TrackDev) * n_tracks, cudaMemcpyHostToDevice, st));
+    if (L.meta_total) CK(cudaMemcpyAsync(c->meta.p, hmeta, L.meta_total, cudaMemcpyHostToDevice, st));
+    CK(cudaMemsetAsync(c->ctrl.p, 0, 8ull * NF + 64, st));
+    CK(cudaEventRecord(c->ev[1], st));
+
+    uint32_t launches = 0;
+    EncodeParams ep;
+    memset(&ep, 0, sizeof ep);
+    ep.tracks = (const TrackDev *)c->tracks.p;
+    ep.frames = (const uint2 *)c->frames.p;
+    ep.n_frames = NF;
+    ep.format = format;
+    ep.level = level;
+    ep.out = out;
+    ep.status = (unsigned long long *)c->ctrl.p;
+    ep.ticket = (uint32_t *)((uint8_t *)c->ctrl.p + 8ull * NF);
+    ep.err = ep.ticket + 1;
+    ep.frame_excl = (unsigned long long *)c->fexcl.p;
+    ep.frame_size = (uint32_t *)c->fsize.p;
+    ep.plane_scratch = (int16_t *)c->plane.p;
+    ep.plane_scratch_elems = plane_elems;
+    ep.cres = (ChanResult *)c->cres.p;
+    ep.report = c->report_on ? (flo_cand_report *)c->report.p : nullptr;
+    ep.smem_plane_bytes = (uint32_t)plane_cap;
+
+    FinalParams fp;
+    memset(&fp, 0, sizeof fp);
+    fp.tracks = ep.tracks; fp.n_tracks = NTR; fp.n_frames = NF; fp.level = level; fp.frames = ep.frames;
+    fp.out = out; fp.meta = (const uint8_t *)c->meta.p;
+    fp.frame_excl = ep.frame_excl; fp.frame_size = ep.frame_size;
+    fp.seg_crc = (uint32_t *)c->segcrc.p; fp.n_segs = NSEG;
+    fp.file_off = (unsigned long long *)c->foff.p;
+    fp.file_len = fp.file_off + n_tracks;
+
+    CK(launch_setup(ep.tracks, NTR, (uint2 *)c->frames.p, NF, st));
+    launches += NF ? 1 : 0;
+    CK(cudaEventRecord(c->ev[2], st));
+    CK(launch_encode(ep, grid, dyn, st));
+    launches += NF ? 1 : 0;
+    CK(cudaEventRecord(c->ev[3], st));
+    CK(launch_toc(fp, st));
+    launches += NF ? 1 : 0;
+    CK(cudaEventRecord(c->ev[4], st));
+    CK(launch_crc_segments(fp, st));
+    launches += NSEG ? 1 : 0;
+    CK(cudaEventRecord(c->ev[5], st));
+    CK(launch_headers(fp, st));
+    launches += 1;
+    CK(cudaEventRecord(c->ev[6], st));
+
+    // results: per-track offsets/lengths + error flag
+    uint64_t *h_off = (uint64_t *)(hs + align_up(sizeof(TrackDev) * n_tracks + L.meta_total, 16));
+    uint32_t *h_err = (uint32_t *)(h_off + 2 * n_tracks);
+    CK(cudaMemcpyAsync(h_off, c->foff.p, 16ull * n_tracks, cudaMemcpyDeviceToHost, st));
+    CK(cudaMemcpyAsync(h_err, ep.err, 4, cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    if (*h_err) { set_err("device-side consistency check failed (code 0x%08x)", *h_err); return FLO_ERR_INTERNAL; }
+    for (size_t t = 0; t < n_tracks; t++) { offsets[t] = h_off[t]; lens[t] = h_off[n_tracks + t]; }
+
+    float t_all = 0, t_enc = 0, t_toc = 0, t_crc = 0, t_hdr = 0, t_setup = 0, t_h2d = 0;
+    cudaEventElapsedTime(&t_h2d, c->ev[0], c->ev[1]);
+    cudaEventElapsedTime(&t_setup, c->ev[1], c->ev[2]);
+    cudaEventElapsedTime(&t_enc, c->ev[2], c->ev[3]);
+    cudaEventElapsedTime(&t_toc, c->ev[3], c->ev[4]);
+    cudaEventElapsedTime(&t_crc, c->ev[4], c->ev[5]);
+    cudaEventElapsedTime(&t_hdr, c->ev[5], c->ev[6]);
+    cudaEventElapsedTime(&t_all, c->ev[1], c->ev[6]);
+    c->ms[0] = t_all; c->ms[1] = t_enc; c->ms[2] = t_crc; c->ms[3] = t_setup + t_toc + t_hdr; c->ms[4] = t_h2d; c->ms[5] = 0;
+    c->launches = launches;
+    return FLO_OK;
+}
+
+extern "C" int flo_encode_batch_device(flo_ctx *c, const flo_track *tracks, size_t n_tracks, int format, uint8_t level,
+                                       void *d_out, size_t d_out_capacity, uint64_t *offsets, uint64_t *lens) {
+    if (!c || (n_tracks && (!tracks || !offsets || !lens)) || !d_out) { set_err("bad argument"); return FLO_ERR_ARG; }
+    std::lock_guard<std::mutex> lk(c->mu);
+    return encode_batch_impl(c, tracks, n_tracks, format, level, false, d_out, d_out_capacity, offsets, lens);
+}
+
+extern "C" int flo_encode_batch(flo_ctx *c, const flo_track *tracks, size_t n_tracks, int format, uint8_t level,
+                                flo_out *outs) {
+    if (!c || (n_tracks && (!tracks || !outs))) { set_err("bad argument"); return FLO_ERR_ARG; }
+    std::lock_guard<std::mutex> lk(c->mu);
+    for (size_t t = 0; t < n_tracks; t++) { outs[t].data = nullptr; outs[t].len = 0; }
+    if (n_tracks == 0) return FLO_OK;
+    std::vector<uint64_t> off(n_tracks), len(n_tracks);
+    int rc = encode_batch_impl(c, tracks, n_tracks, format, level, true, nullptr, 0, off.data(), len.data());
+    if (rc) return rc;
+    // one D2H of the compact image region, then split per track
+    uint64_t total = 0;
+    for (size_t t = 0; t < n_tracks; t++) total = std::max(total, off[t] + len[t]);
+    if ((rc = c->h_out.reserve(total + 16))) return rc;
+    cudaStream_t st = c->stream;
+    CK(cudaEventRecord(c->ev[0], st));
+    CK(cudaMemcpyAsync(c->h_out.p, c->out.p, total, cudaMemcpyDeviceToHost, st));
+    CK(cudaEventRecord(c->ev[1], st));
+    CK(cudaStreamSynchronize(st));
+    cudaEventElapsedTime(&c->ms[5], c->ev[0], c->ev[1]);
+    for (size_t t = 0; t < n_tracks; t++) {
+        uint8_t *b = (uint8_t *)malloc(len[t] ? len[t] : 1);
+        if (!b) {
+            for (size_t u = 0; u < t; u++) { free(outs[u].data); outs[u].data = nullptr; outs[u].len = 0; }
+            set_err("out of host memory");
+            return FLO_ERR_NOMEM;
+        }
+        memcpy(b, (const uint8_t *)c->h_out.p + off[t], len[t]);
+        outs[t].data = b;
+        outs[t].len = (size_t)len[t];
+    }
+    return FLO_OK;
+}
+
+static int encode_one(flo_ctx *c, const void *samples, size_t n, int format, uint32_t sr, uint8_t ch, uint8_t bits,
+                      uint8_t level, const uint8_t *meta, size_t meta_len, uint8_t **out, size_t *out_len) {
+    if (!c || !out || !out_len) { set_err("bad argument"); return FLO_ERR_ARG; }
+    *out = nullptr; *out_len = 0;
+    flo_track t;
+    t.samples = samples; t.n_interleaved = n; t.sample_rate = sr; t.channels = ch; t.bit_depth = bits;
+    t.meta = meta; t.meta_len = meta_len;
+    flo_out o = {nullptr, 0};
+    int rc = flo_encode_batch(c, &t, 1, format, level, &o);
+    if (rc) return rc;
+    *out = o.data; *out_len = o.len;
+    return FLO_OK;
+}
+
+extern "C" int flo_encode(flo_ctx *c, const float *samples, size_t n, uint32_t sr, uint8_t ch, uint8_t bits, uint8_t level,
+                          const uint8_t *meta, size_t meta_len, uint8_t **out, size_t *out_len) {
+    return encode_one(c, samples, n, FLO_FMT_F32, sr, ch, bits, level, meta, meta_len, out, out_len);
+}
+extern "C" int flo_encode_pcm16(flo_ctx *c, const int16_t *pcm, size_t n, uint32_t sr, uint8_t ch, uint8_t bits,
+                                uint8_t level, const uint8_t *meta, size_t meta_len, uint8_t **out, size_t *out_len) {
+    return encode_one(c, pcm, n, FLO_FMT_PCM16, sr, ch, bits, level, meta, meta_len, out, out_len);
+}

@@ -1,0 +1,93 @@
+// flo_internal.h -- structures shared by the kernels (flo_kernels.cu) and the
+// host side of the C ABI (flo_api.cu).  Not part of the public interface.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "../../include/flo_b200.h"
+
+namespace flo {
+
+constexpr int NT = 512;               // threads per CTA of the frame-encode kernel
+constexpr int NWARP = NT / 32;
+constexpr int CH = 16;                // samples per thread chunk
+constexpr int RING_WORDS = 4096;      // bit-packer staging ring (16 KB)
+constexpr int MAXORD = 12;
+constexpr int NCAND = 14;             // raw, fixed 0..4, lpc 5..12
+constexpr int REPORT_CH = 8;          // channels per frame covered by the parity report
+constexpr uint32_t FILE_HDR = 70;     // magic(4) + header(66), writer.rs:132-191
+constexpr uint32_t CRC_SEG = 65536;   // bytes of DATA per CRC segment
+constexpr int CRC_NT = 256;
+
+// One track of the batch (device copy).
+struct TrackDev {
+    const void *samples;              // device pointer, interleaved f32 or i16
+    unsigned long long n_inter;       // interleaved samples
+    unsigned long long static_off;    // bytes of all earlier tracks' header+TOC+meta (file start = static_off + excl[first_frame])
+    unsigned long long meta_off;      // into the metadata arena
+    unsigned long long meta_len;
+    uint32_t sample_rate;
+    uint32_t channels;
+    uint32_t bit_depth;
+    uint32_t first_frame;             // global index of this track's first frame
+    uint32_t n_frames;
+    uint32_t first_seg;               // first CRC segment slot of this track
+};
+
+// Winner of the predictor search for one channel of one frame.
+struct ChanResult {
+    int32_t kind;                     // 0 raw, 1 fixed, 2 lpc, 3 empty
+    int32_t order;
+    int32_t k;
+    uint32_t nbytes;                  // residual payload bytes
+    int32_t coef[MAXORD];
+    int32_t shift;                    // LPC shift_bits (lpc.rs:266-268; always 15 in practice)
+    int32_t pad[3];
+};
+
+struct EncodeParams {
+    const TrackDev *tracks;
+    const uint2 *frames;              // per global frame: {track, frame index in track}
+    uint32_t n_frames;
+    int format;                       // FLO_FMT_*
+    int level;                        // 0..9
+    uint8_t *out;                     // output arena
+    unsigned long long *status;       // decoupled look-back words, one per frame (zeroed)
+    uint32_t *ticket;                 // dynamic frame counter (zeroed)
+    unsigned long long *frame_excl;   // out: exclusive prefix of frame sizes (global)
+    uint32_t *frame_size;             // out
+    int16_t *plane_scratch;           // per-CTA global sample planes for frames too large for shared memory
+    unsigned long long plane_scratch_elems;  // int16 elements per CTA
+    ChanResult *cres;                 // per-CTA channel results, 256 entries per CTA
+    flo_cand_report *report;          // optional [n_frames][REPORT_CH][NCAND]
+    uint32_t *err;                    // device error flag
+    uint32_t smem_plane_bytes;        // bytes of dynamic shared memory available for sample planes
+};
+
+struct FinalParams {
+    const TrackDev *tracks;
+    uint32_t n_tracks;
+    uint32_t n_frames;
+    int level;
+    const uint2 *frames;
+    uint8_t *out;
+    const uint8_t *meta;              // metadata arena
+    const unsigned long long *frame_excl;
+    const uint32_t *frame_size;
+    uint32_t *seg_crc;                // per CRC segment
+    uint32_t n_segs;
+    unsigned long long *file_off;     // out: per track
+    unsigned long long *file_len;     // out: per track
+};
+
+// kernel launchers (flo_kernels.cu)
+size_t encode_static_smem();
+cudaError_t launch_setup(const TrackDev *tracks, uint32_t n_tracks, uint2 *frames, uint32_t n_frames, cudaStream_t st);
+cudaError_t launch_encode(const EncodeParams &p, int grid, size_t dyn_smem, cudaStream_t st);
+cudaError_t launch_toc(const FinalParams &p, cudaStream_t st);
+cudaError_t launch_crc_segments(const FinalParams &p, cudaStream_t st);
+cudaError_t launch_headers(const FinalParams &p, cudaStream_t st);
+cudaError_t configure_encode_kernel(size_t dyn_smem);
+void upload_crc_tables();
+
+}  // namespace flo

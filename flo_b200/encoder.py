@@ -1,0 +1,199 @@
+"""Host-side mirror of the reference's lossless encoder interface over the C ABI.
+
+    Encoder(sample_rate, channels, bit_depth).with_compression(level).encode(samples, metadata) -> bytes
+
+is `libflo_audio::Encoder::{new, with_compression, encode}` (libflo/src/lossless/encoder.rs:17-45,
+Docs/rust-api.md:44-73) with the same argument meaning and the same bytes out.  Everything is
+computed by the CUDA kernels behind include/flo_b200.h; there is no CPU path.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import threading
+from dataclasses import dataclass
+from typing import List, Optional, Sequence, Tuple
+
+import numpy as np
+
+from . import _lib
+from ._lib import FMT_F32, FMT_PCM16, FloError
+
+
+class Context:
+    """One GPU + its streams and scratch arenas (flo_ctx)."""
+
+    def __init__(self, device: int = 0):
+        self._L = _lib.lib()
+        h = C.c_void_p()
+        _lib.check(self._L.flo_ctx_create(int(device), C.byref(h)))
+        self._h = h
+        self.device = int(device)
+
+    def close(self) -> None:
+        if getattr(self, "_h", None):
+            self._L.flo_ctx_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # -- configuration ---------------------------------------------------------------
+    def set_stream(self, cuda_stream: int) -> None:
+        _lib.check(self._L.flo_ctx_set_stream(self._h, C.c_void_p(int(cuda_stream) or None)))
+
+    def enable_report(self, on: bool = True) -> None:
+        _lib.check(self._L.flo_ctx_enable_report(self._h, int(on)))
+
+    def read_report(self, frame: int, channel: int) -> List[Tuple[int, int]]:
+        """[(k, size)] for candidates raw, fixed 0..4, lpc 5..12 (size -1 = absent)."""
+        buf = (_lib.CandReport * 14)()
+        _lib.check(self._L.flo_ctx_read_report(self._h, frame, channel, buf))
+        return [(int(b.k), int(b.size)) for b in buf]
+
+    def last_timing(self) -> dict:
+        ms = (C.c_float * 6)()
+        n = C.c_uint32()
+        _lib.check(self._L.flo_ctx_last_timing(self._h, ms, C.byref(n)))
+        keys = ["device_ms", "encode_ms", "crc_ms", "misc_ms", "h2d_ms", "d2h_ms"]
+        d = {k: float(v) for k, v in zip(keys, ms)}
+        d["launches"] = int(n.value)
+        return d
+
+    # -- encode entries ----------------------------------------------------------------
+    def encode_batch(self, tracks: Sequence["TrackSpec"], level: int = 5, fmt: int = FMT_F32) -> List[bytes]:
+        n = len(tracks)
+        if n == 0:
+            return []
+        arr = (_lib.Track * n)()
+        keep = []
+        dt = np.float32 if fmt == FMT_F32 else np.int16
+        for i, t in enumerate(tracks):
+            s = np.ascontiguousarray(t.samples, dtype=dt).reshape(-1)
+            m = bytes(t.metadata or b"")
+            mb = C.create_string_buffer(m, len(m)) if m else None
+            keep.append((s, mb))
+            arr[i].samples = s.ctypes.data if s.size else None
+            arr[i].n_interleaved = s.size
+            arr[i].sample_rate = _u(t.sample_rate, 32, "sample_rate")
+            arr[i].channels = _u(t.channels, 8, "channels")
+            arr[i].bit_depth = _u(t.bit_depth, 8, "bit_depth")
+            arr[i].meta = C.addressof(mb) if mb is not None else None
+            arr[i].meta_len = len(m)
+        outs = (_lib.Out * n)()
+        _lib.check(self._L.flo_encode_batch(self._h, arr, n, fmt, min(int(level), 255), outs))
+        res = []
+        for o in outs:
+            res.append(C.string_at(o.data, o.len) if o.len else b"")
+            self._L.flo_free(o.data)
+        return res
+
+    def encode_batch_device(self, dev_ptrs: Sequence[int], n_interleaved: Sequence[int], sample_rate: Sequence[int],
+                            channels: Sequence[int], bit_depth: Sequence[int], d_out: int, d_out_capacity: int,
+                            level: int = 5, fmt: int = FMT_F32, metadata: Optional[Sequence[bytes]] = None):
+        """Device-resident batch: inputs and the output arena stay in HBM.  Returns (offsets, lens)."""
+        n = len(dev_ptrs)
+        arr = (_lib.Track * n)()
+        keep = []
+        for i in range(n):
+            m = bytes(metadata[i]) if metadata is not None and metadata[i] else b""
+            mb = C.create_string_buffer(m, len(m)) if m else None
+            keep.append(mb)
+            arr[i].samples = int(dev_ptrs[i]) or None
+            arr[i].n_interleaved = int(n_interleaved[i])
+            arr[i].sample_rate = int(sample_rate[i])
+            arr[i].channels = int(channels[i])
+            arr[i].bit_depth = int(bit_depth[i])
+            arr[i].meta = C.addressof(mb) if mb is not None else None
+            arr[i].meta_len = len(m)
+        off = np.zeros(n, np.uint64)
+        ln = np.zeros(n, np.uint64)
+        _lib.check(self._L.flo_encode_batch_device(
+            self._h, arr, n, fmt, min(int(level), 255), C.c_void_p(int(d_out)), int(d_out_capacity),
+            off.ctypes.data_as(C.POINTER(C.c_uint64)), ln.ctypes.data_as(C.POINTER(C.c_uint64))))
+        return off, ln
+
+    def output_bound(self, n_interleaved: Sequence[int], sample_rate: Sequence[int], channels: Sequence[int],
+                     meta_len: Optional[Sequence[int]] = None) -> int:
+        n = len(n_interleaved)
+        arr = (_lib.Track * n)()
+        for i in range(n):
+            arr[i].n_interleaved = int(n_interleaved[i])
+            arr[i].sample_rate = int(sample_rate[i])
+            arr[i].channels = int(channels[i])
+            arr[i].bit_depth = 16
+            arr[i].samples = 16 if n_interleaved[i] else None       # never dereferenced by the bound
+            arr[i].meta_len = 0
+        extra = int(sum(meta_len)) if meta_len is not None else 0
+        b = int(self._L.flo_output_bound(arr, n))
+        if b == 0:
+            raise FloError(_lib.last_error())
+        return b + extra
+
+
+def _u(v: int, bits: int, name: str) -> int:
+    v = int(v)
+    if v < 0 or v >= (1 << bits):
+        raise FloError(f"{name}={v} does not fit u{bits}")
+    return v
+
+
+@dataclass
+class TrackSpec:
+    samples: np.ndarray            # interleaved f32 (or int16 for the PCM16 entry)
+    sample_rate: int
+    channels: int
+    bit_depth: int = 16
+    metadata: bytes = b""
+
+
+_ctx_lock = threading.Lock()
+_ctxs: dict = {}
+
+
+def default_context(device: int = 0) -> Context:
+    with _ctx_lock:
+        c = _ctxs.get(device)
+        if c is None:
+            c = _ctxs[device] = Context(device)
+        return c
+
+
+class Encoder:
+    """libflo_audio::Encoder (libflo/src/lossless/encoder.rs:9-45)."""
+
+    def __init__(self, sample_rate: int = 44100, channels: int = 1, bit_depth: int = 16, *, device: int = 0,
+                 context: Optional[Context] = None):
+        # Default = (44100, 1, 16): Docs/rust-api.md, impl Default for Encoder
+        self.sample_rate = _u(sample_rate, 32, "sample_rate")
+        self.channels = _u(channels, 8, "channels")
+        self.bit_depth = _u(bit_depth, 8, "bit_depth")
+        self.compression_level = 5                          # encoder.rs:22
+        self._device = device
+        self._ctx = context
+
+    def with_compression(self, level: int) -> "Encoder":
+        self.compression_level = min(_u(level, 8, "level"), 9)   # encoder.rs:26-29
+        return self
+
+    def _context(self) -> Context:
+        if self._ctx is None:
+            self._ctx = default_context(self._device)
+        return self._ctx
+
+    def encode(self, samples, metadata: bytes = b"") -> bytes:
+        """Encoder::encode(&self, samples: &[f32], metadata: &[u8]) -> FloResult<Vec<u8>> (encoder.rs:32-45)."""
+        t = TrackSpec(np.asarray(samples, dtype=np.float32), self.sample_rate, self.channels, self.bit_depth, metadata)
+        return self._context().encode_batch([t], self.compression_level, FMT_F32)[0]
+
+    def encode_pcm16(self, pcm, metadata: bytes = b"") -> bytes:
+        """reflo's S16 ingest (reflo/src/audio.rs:247-254) + Encoder::encode, fused on the device."""
+        t = TrackSpec(np.asarray(pcm, dtype=np.int16), self.sample_rate, self.channels, self.bit_depth, metadata)
+        return self._context().encode_batch([t], self.compression_level, FMT_PCM16)[0]
+
+
+def encode_batch(tracks: Sequence[TrackSpec], level: int = 5, fmt: int = FMT_F32, device: int = 0) -> List[bytes]:
+    """Loop of Encoder::encode over tracks (reflo/src/main.rs:218-276) as one device pass."""
+    return default_context(device).encode_batch(tracks, min(int(level), 9), fmt)

@@ -1,0 +1,133 @@
+/*
+ * flo_b200.h -- C ABI of the B200-native lossless ALPC encoder for the flo format.
+ *
+ * This is the drop-in boundary for ONE path of flo-audio/flo: the lossless
+ * encode path behind
+ *
+ *     libflo_audio::Encoder::new(sample_rate, channels, bit_depth)
+ *                  .with_compression(level)
+ *                  .encode(samples: &[f32], metadata: &[u8]) -> FloResult<Vec<u8>>
+ *
+ * (reference: libflo/src/lossless/encoder.rs:17-45, re-exported at
+ * libflo/src/lib.rs:20, documented in Docs/rust-api.md:44-73, called by
+ * reflo/src/lib.rs:301-305).  A Rust `Encoder` shim binds these symbols with
+ * `extern "C"` (see INTEGRATION.md and rust/); the bytes returned are
+ * identical to what the reference encoder returns for the same arguments.
+ *
+ * Plain pointers and sizes only; no torch / CUDA types in any signature.
+ * There is NO CPU fallback: every entry point fails (non-zero return,
+ * message via flo_last_error) when no CUDA device is usable.
+ *
+ * Return value of every int function: 0 = ok, non-zero = error
+ * (FLO_ERR_*); the shim maps that to Err(String) with flo_last_error().
+ */
+#ifndef FLO_B200_H
+#define FLO_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define FLO_OK            0
+#define FLO_ERR_ARG       1   /* bad argument (channels == 0 / sample_rate == 0: the reference panics, encoder.rs:48-50) */
+#define FLO_ERR_CUDA      2   /* CUDA runtime / driver error, or no device */
+#define FLO_ERR_NOMEM     3   /* host or device allocation failed */
+#define FLO_ERR_INTERNAL  4   /* device-side consistency check failed */
+
+/* sample formats of the batched entries */
+#define FLO_FMT_F32    0      /* interleaved f32, the documented Encoder::encode input (encoder.rs:32) */
+#define FLO_FMT_PCM16  1      /* interleaved i16 PCM: reflo's S16 ingest arm, s * (1/32768) (reflo/src/audio.rs:247-254), then as F32 */
+
+typedef struct flo_ctx flo_ctx;
+
+/* One context = one GPU + its streams and scratch arenas.  Calls on one
+ * context serialise on an internal mutex; distinct contexts are independent
+ * (the Rust Encoder stays Send + Sync by holding Arc<ctx>, Docs/rust-api.md:374-378). */
+int  flo_ctx_create(int device, flo_ctx **out);
+void flo_ctx_destroy(flo_ctx *ctx);
+
+/* Encoder::new(sr, ch, bits).with_compression(level).encode(samples, metadata)
+ * (libflo/src/lossless/encoder.rs:17-45).  `level` is clamped to 9 like
+ * with_compression (encoder.rs:26-29).  *out is allocated by the library
+ * (release with flo_free); inputs are borrowed for the call only. */
+int flo_encode(flo_ctx *ctx, const float *samples, size_t n_interleaved,
+               uint32_t sample_rate, uint8_t channels, uint8_t bit_depth, uint8_t level,
+               const uint8_t *meta, size_t meta_len, uint8_t **out, size_t *out_len);
+
+/* reflo's 16-bit ingest (reflo/src/audio.rs:247-254) fused in front of
+ * flo_encode: identical bytes to flo_encode(f32(pcm) * (1/32768)). */
+int flo_encode_pcm16(flo_ctx *ctx, const int16_t *pcm, size_t n_interleaved,
+                     uint32_t sample_rate, uint8_t channels, uint8_t bit_depth, uint8_t level,
+                     const uint8_t *meta, size_t meta_len, uint8_t **out, size_t *out_len);
+
+/* Batched entry (additive; the reference has no batch call -- it is a loop of
+ * Encoder::encode over tracks, reflo/src/main.rs:218-276).  Frames of all
+ * tracks are encoded in one device pass.  Every track gets exactly the bytes
+ * flo_encode would return for it. */
+typedef struct {
+    const void    *samples;        /* interleaved f32 or i16 (see `format` of the call) */
+    size_t         n_interleaved;  /* number of interleaved samples (frames * channels [+ ragged tail]) */
+    uint32_t       sample_rate;
+    uint8_t        channels;
+    uint8_t        bit_depth;      /* copied to the header only (encoder.rs:40, writer.rs:163) */
+    const uint8_t *meta;           /* opaque metadata bytes appended verbatim (writer.rs:96), may be NULL */
+    size_t         meta_len;
+} flo_track;
+
+typedef struct {
+    uint8_t *data;                 /* library-allocated .flo file image (flo_free) */
+    size_t   len;
+} flo_out;
+
+int flo_encode_batch(flo_ctx *ctx, const flo_track *tracks, size_t n_tracks, int format,
+                     uint8_t level, flo_out *outs);
+
+/* Device-resident variant: tracks[i].samples are DEVICE pointers on the
+ * context's GPU (meta stays a host pointer); the concatenated file images are
+ * written to the device buffer d_out (capacity >= flo_output_bound).  The
+ * image of track i is d_out[offsets[i] .. offsets[i] + lens[i]); offsets/lens
+ * are host arrays of n_tracks entries.  The call returns after the device
+ * work finished. */
+int flo_encode_batch_device(flo_ctx *ctx, const flo_track *tracks, size_t n_tracks, int format,
+                            uint8_t level, void *d_out, size_t d_out_capacity,
+                            uint64_t *offsets, uint64_t *lens);
+
+/* Worst-case total size of the file images of a batch (raw-coded frames). */
+size_t flo_output_bound(const flo_track *tracks, size_t n_tracks);
+
+/* Run the device work of this context on a caller-owned CUDA stream
+ * (a cudaStream_t / CUstream passed as void*; NULL = the context's own). */
+int flo_ctx_set_stream(flo_ctx *ctx, void *cuda_stream);
+
+/* Timing of the last batch call, measured with CUDA events on the stream the
+ * kernels ran on.  ms[0] = whole device pass (first kernel .. last kernel),
+ * ms[1] = frame-encode kernel, ms[2] = CRC kernels, ms[3] = setup/finalise
+ * kernels, ms[4] = H2D copies, ms[5] = D2H copies.  launches = kernels
+ * launched by that call. */
+int flo_ctx_last_timing(flo_ctx *ctx, float ms[6], uint32_t *launches);
+
+/* Per-frame analysis report of the last batch call, for parity tests: for
+ * global frame g and channel c (< 8), candidate j (raw, fixed 0..4, lpc
+ * 5..12 -> j = 0..13): k and encoded size (-1 = candidate absent).  Must be
+ * enabled before the call; costs a little device memory. */
+typedef struct { int32_t k; int32_t pad; int64_t size; } flo_cand_report;
+int flo_ctx_enable_report(flo_ctx *ctx, int enable);
+int flo_ctx_read_report(flo_ctx *ctx, uint32_t frame, uint32_t channel, flo_cand_report out[14]);
+
+/* Pinned host memory (optional; speeds up the host<->device copies of
+ * flo_encode / flo_encode_batch when inputs live in it). */
+void *flo_host_alloc(size_t bytes);
+void  flo_host_free(void *p);
+
+void        flo_free(void *p);
+const char *flo_last_error(void);      /* thread-local, never NULL */
+const char *flo_version(void);
+int         flo_device_count(void);    /* 0 when no usable CUDA device */
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* FLO_B200_H */

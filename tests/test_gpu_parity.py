@@ -1,0 +1,274 @@
+"""Parity of the CUDA path against the oracle and the reference's golden bitstreams.
+
+Every test calls through the C ABI (include/flo_b200.h) via flo_b200's ctypes mirror of the
+reference's Encoder.  The bar is byte identity of the whole .flo image."""
+import struct
+import zlib
+
+import numpy as np
+import pytest
+
+from helpers import (LOSSLESS_EXAMPLES, file_to_f32_input, golden_audio_wav_f32, golden_bytes, oracle, pcm16_to_f32,
+                     synth_pcm16)
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def fb():
+    import flo_b200
+    return flo_b200
+
+
+@pytest.fixture(scope="module")
+def ctx(fb):
+    c = fb.default_context(0)
+    return c
+
+
+def first_diff(a: bytes, b: bytes) -> str:
+    n = min(len(a), len(b))
+    for i in range(n):
+        if a[i] != b[i]:
+            return f"len {len(a)} vs {len(b)}, first difference at byte {i}: {a[i:i+8].hex()} vs {b[i:i+8].hex()}"
+    return f"len {len(a)} vs {len(b)}, common prefix equal"
+
+
+def check_same(got: bytes, want: bytes, what=""):
+    assert got == want, f"{what}: {first_diff(got, want)}"
+
+
+def explain(ctx, x, sr, ch, level):
+    """Candidate-level diff against the oracle for the first frames (diagnostics on failure)."""
+    lines = []
+    q = (np.asarray(x, np.float32) * np.float32(32767.0)).clip(-32768, 32767)
+    q = np.nan_to_num(q, nan=0.0).astype(np.int64)
+    nfr = -(-(len(x) // ch) // sr)
+    for g in range(min(2, nfr)):
+        fr = q[g * sr * ch:(g + 1) * sr * ch]
+        chans = [fr[c::ch] for c in range(ch)]
+        if ch == 2:
+            m = min(len(chans[0]), len(chans[1]))
+            l, r = chans[0][:m], chans[1][:m]
+            if int(((l - r) ** 2).sum()) < (int((l * l).sum()) + int((r * r).sum())) // 2:
+                chans = [l + r, l - r]
+        for c in range(min(ch, 8)):
+            rep = ctx.read_report(g, c)
+            cands = oracle.channel_candidates(chans[c].astype(np.int32), level)
+            for cd in cands:
+                j = 0 if cd["kind"] == 0 else 1 + cd["order"]
+                flag = "" if (rep[j][1] == cd["size"] and (cd["kind"] == 0 or cd["size"] < 0 or rep[j][0] == cd["k"])) else "   <-- MISMATCH"
+                lines.append(f"frame {g} ch {c} cand {j}: gpu (k,size)={rep[j]} oracle (k,size)=({cd['k']},{cd['size']}){flag}")
+    return "\n".join(lines)
+
+
+# ---- golden bitstreams of the reference ------------------------------
+@pytest.mark.parametrize("name", LOSSLESS_EXAMPLES)
+def test_examples_whole_file(fb, name):
+    gold = golden_bytes(name)
+    f = oracle.FloFile(gold)
+    x = file_to_f32_input(f)
+    meta = gold[len(gold) - f.meta_size:] if f.meta_size else b""
+    out = fb.Encoder(f.sample_rate, f.channels, f.bit_depth).with_compression(f.level).encode(x, meta)
+    check_same(out, gold, name)
+
+
+def test_audio_wav_config1(fb):
+    x, sr, ch = golden_audio_wav_f32()
+    gold = golden_bytes("audio_lossless.flo")
+    out = fb.Encoder(sr, ch, 16).encode(x, b"")
+    assert len(out) == 108 and out[:62] == gold[:62] and out[70:108] == gold[70:108]
+    check_same(fb.Encoder(sr, ch, 16).encode(x, gold[108:]), gold, "audio.wav with reference metadata")
+
+
+# ---- oracle parity on seeded synthetic signals ---------------------------------------------
+CASES = [
+    # (n sample-frames, channels, sample_rate, kind, noise_lsb)
+    (3 * 44100 + 17, 2, 44100, "multitone", 64),
+    (2 * 44100, 1, 44100, "multitone", 8),
+    (3 * 8000 + 5, 1, 8000, "speech", 16),
+    (48000 + 1000, 2, 48000, "multitone", 512),
+    (96000 + 333, 2, 96000, "sweep", 32),          # frame does not fit shared memory -> global-plane path
+    (2 * 96000, 1, 96000, "sweep", 4),
+    (2 * 22050 + 1, 2, 22050, "tone", 2),
+    (1500, 6, 1000, "multitone", 64),
+    (3000, 3, 8000, "speech", 128),
+]
+
+
+@pytest.mark.parametrize("case", CASES, ids=lambda c: f"{c[2]}Hz-{c[1]}ch-{c[3]}")
+@pytest.mark.parametrize("level", [5, 9])
+def test_f32_entry_matches_oracle(fb, ctx, case, level):
+    n, ch, sr, kind, noise = case
+    pcm = synth_pcm16(n, ch, sr, seed=0xF10 + n, kind=kind, noise_lsb=noise)
+    x = pcm16_to_f32(pcm)
+    want = oracle.encode(x, sr, ch, 16, level, b"meta-bytes")
+    ctx.enable_report(True)
+    got = fb.Encoder(sr, ch, 16, context=ctx).with_compression(level).encode(x, b"meta-bytes")
+    if got != want:
+        pytest.fail(first_diff(got, want) + "\n" + explain(ctx, x, sr, ch, level))
+    ctx.enable_report(False)
+
+
+@pytest.mark.parametrize("level", range(10))
+def test_all_levels_stereo_midside(fb, level):
+    pcm = synth_pcm16(2 * 8000 + 123, 2, 8000, seed=level)
+    x = pcm16_to_f32(pcm)
+    want = oracle.encode(x, 8000, 2, 24, level, b"m")
+    got = fb.Encoder(8000, 2, 24).with_compression(level).encode(x, b"m")
+    check_same(got, want, f"level {level}")
+    f = oracle.FloFile(got)
+    assert any(fr.flags & 1 for fr in f.frames)
+
+
+def test_level_above_9_clamps(fb):
+    x = pcm16_to_f32(synth_pcm16(5000, 1, 8000, seed=1))
+    assert fb.Encoder(8000, 1, 16).with_compression(200).encode(x, b"") == oracle.encode(x, 8000, 1, 16, 9, b"")
+
+
+def test_pcm16_entry_matches_oracle(fb):
+    for ch, sr in ((2, 44100), (1, 8000)):
+        pcm = synth_pcm16(sr + 77, ch, sr, seed=5)
+        pcm[:7] = [32767, -32768, 1, -1, 0, 2, -2][:7]
+        want = oracle.encode_pcm16(pcm, sr, ch, 16, 5, b"")
+        got = fb.Encoder(sr, ch, 16).encode_pcm16(pcm, b"")
+        check_same(got, want, f"pcm16 {ch}ch")
+        check_same(got, fb.Encoder(sr, ch, 16).encode(pcm16_to_f32(pcm), b""), "pcm16 vs f32 entry")
+
+
+def test_pcm16_all_values(fb):
+    """Exhaustive over the 65536 PCM values: ingest + quantise chain (audio.rs:247-254, audio_constants.rs:18-20)."""
+    pcm = np.arange(-32768, 32768, dtype=np.int32).astype(np.int16)
+    want = oracle.encode_pcm16(pcm, 65536, 1, 16, 0, b"")
+    got = fb.Encoder(65536, 1, 16).with_compression(0).encode_pcm16(pcm, b"")
+    check_same(got, want, "all pcm values")
+
+
+@pytest.mark.parametrize("n", [0, 1, 2, 3, 4, 5, 6, 13, 15, 16, 17, 31, 33, 8191, 8192, 8193, 44099, 44100, 44101, 88200, 88201])
+def test_frame_boundary_lengths(fb, n):
+    pcm = synth_pcm16(n, 1, 44100, seed=n)
+    x = pcm16_to_f32(pcm)
+    check_same(fb.Encoder(44100, 1, 16).encode(x, b""), oracle.encode(x, 44100, 1, 16, 5, b""), f"n={n}")
+
+
+@pytest.mark.parametrize("n_inter", [1, 2, 3, 5, 2001, 16001, 16002, 16003])
+def test_odd_interleaved_length_stereo(fb, n_inter):
+    x = pcm16_to_f32(synth_pcm16(n_inter // 2 + 1, 2, 8000, seed=n_inter))[:n_inter]
+    check_same(fb.Encoder(8000, 2, 16).encode(x, b""), oracle.encode(x, 8000, 2, 16, 5, b""), f"n_inter={n_inter}")
+
+
+def test_ragged_multichannel(fb):
+    x = pcm16_to_f32(synth_pcm16(1000, 5, 300, seed=2))[:4998]
+    check_same(fb.Encoder(300, 5, 16).encode(x, b"xy"), oracle.encode(x, 300, 5, 16, 5, b"xy"), "5ch ragged")
+
+
+def test_nan_inf_and_clipping(fb):
+    x = np.array([np.nan, np.inf, -np.inf, 0.25, 1.5, -1.5, 1.0, -1.0, 1e-8, -1e-8, 3e-5, -3e-5] * 40, np.float32)
+    for ch in (1, 2):
+        check_same(fb.Encoder(100, ch, 16).encode(x, b""), oracle.encode(x, 100, ch, 16, 5, b""), f"nan {ch}ch")
+
+
+def test_silence_and_mixed_frames(fb):
+    sr = 8000
+    loud = pcm16_to_f32(synth_pcm16(sr, 2, sr, seed=3))
+    quiet = np.zeros(2 * sr, np.float32)
+    tiny = np.full(2 * sr, 5e-8, np.float32)                   # below the 1e-7 silence threshold
+    near = np.full(2 * sr, 2e-7, np.float32)                   # above it, quantises to 0 -> fixed-0 k=0 "raw" frame
+    x = np.concatenate([quiet, loud, tiny, near, loud[:1000]])
+    want = oracle.encode(x, sr, 2, 16, 5, b"")
+    got = fb.Encoder(sr, 2, 16).encode(x, b"")
+    check_same(got, want, "mixed")
+    f = oracle.FloFile(got)
+    assert [fr.frame_type for fr in f.frames][:4] == [0, 8, 0, 254]
+
+
+def test_white_noise_goes_raw(fb):
+    rng = np.random.default_rng(7)
+    pcm = rng.integers(-32768, 32768, 2 * 20000, dtype=np.int64).astype(np.int16)
+    x = pcm16_to_f32(pcm)
+    want = oracle.encode(x, 20000, 2, 16, 5, b"")
+    check_same(fb.Encoder(20000, 2, 16).encode(x, b""), want, "noise")
+
+
+def test_long_unary_runs(fb):
+    """Spiky residuals: a few huge samples in near-silence force q up to 255 (rice.rs:100-108)."""
+    pcm = np.zeros(30000, np.int16)
+    pcm[::997] = 32767
+    pcm[5::1999] = -32768
+    x = pcm16_to_f32(pcm)
+    for level in (0, 2, 5):
+        check_same(fb.Encoder(30000, 1, 16).with_compression(level).encode(x, b""),
+                   oracle.encode(x, 30000, 1, 16, level, b""), f"spikes L{level}")
+
+
+def test_batch_mixed_tracks(fb, ctx):
+    specs, want = [], []
+    for i, (n, ch, sr, lvl_meta) in enumerate([(9000, 1, 8000, b"a"), (44100 + 5, 2, 44100, b""), (0, 2, 44100, b"zz"),
+                                               (700, 4, 500, b"meta" * 50), (1, 1, 44100, b""), (96000, 2, 96000, b"q")]):
+        pcm = synth_pcm16(n, ch, sr, seed=40 + i)
+        x = pcm16_to_f32(pcm)
+        specs.append(fb.TrackSpec(x, sr, ch, 16 + i, lvl_meta))
+        want.append(oracle.encode(x, sr, ch, 16 + i, 5, lvl_meta))
+    got = ctx.encode_batch(specs, 5)
+    for i, (g, w) in enumerate(zip(got, want)):
+        check_same(g, w, f"track {i}")
+
+
+def test_candidate_report_matches_oracle(fb, ctx):
+    """Per-candidate (k, size) of the analysis stage equals the oracle's exhaustive search."""
+    sr = 16000
+    pcm = synth_pcm16(sr, 1, sr, seed=11, noise_lsb=32)
+    x = pcm16_to_f32(pcm)
+    ints = np.array([oracle.f32_to_i32(float(v)) for v in x], dtype=np.int32)
+    for level in (5, 9):
+        ctx.enable_report(True)
+        fb.Encoder(sr, 1, 16, context=ctx).with_compression(level).encode(x, b"")
+        rep = ctx.read_report(0, 0)
+        ctx.enable_report(False)
+        cands = oracle.channel_candidates(ints, level)
+        for cd in cands:
+            j = 0 if cd["kind"] == 0 else 1 + cd["order"]
+            assert rep[j][1] == cd["size"], (level, cd, rep[j])
+            if cd["size"] >= 0 and cd["kind"] != 0:
+                assert rep[j][0] == cd["k"], (level, cd, rep[j])
+
+
+def test_decoded_samples_bit_exact(fb):
+    """Round trip through the restated reference decoder (decoder.rs) gives the quantised input back."""
+    sr, ch = 44100, 2
+    pcm = synth_pcm16(2 * sr + 100, ch, sr, seed=21)
+    x = pcm16_to_f32(pcm)
+    out = fb.Encoder(sr, ch, 16).encode(x, b"")
+    want = (x * np.float32(32767.0)).clip(-32768, 32767).astype(np.int32)
+    assert np.array_equal(oracle.decode_i32(out), want)
+    f = oracle.FloFile(out)
+    assert zlib.crc32(f.data_chunk()) == f.crc32
+
+
+def test_one_hour_shape_properties(fb, ctx):
+    """BASELINE config 2 at reduced length (120 s): container invariants that do not need the oracle."""
+    sr, ch, secs = 44100, 2, 120
+    pcm = synth_pcm16(sr * secs, ch, sr, seed=0xF11)
+    out = fb.Encoder(sr, ch, 16, context=ctx).encode_pcm16(pcm, b"")
+    f = oracle.FloFile(out)
+    assert f.num_frames == secs and f.total_samples == sr * secs
+    assert zlib.crc32(f.data_chunk()) == f.crc32
+    off = 0
+    for i, fr in enumerate(f.frames):
+        assert fr.byte_offset == off and fr.timestamp_ms == 1000 * i
+        off += fr.frame_size
+    assert off == f.data_size
+    want = pcm.astype(np.int32) - np.sign(pcm).astype(np.int32)      # ingest + quantise shrinks |s| by one LSB
+    assert np.array_equal(oracle.decode_i32(out), want)
+    # spot-check 3 frames byte-for-byte against the oracle
+    for i in (0, 57, secs - 1):
+        seg = pcm[i * sr * ch:(i + 1) * sr * ch]
+        ref = oracle.FloFile(oracle.encode_pcm16(seg, sr, ch, 16, 5, b""))
+        assert f.frame_bytes(i) == ref.frame_bytes(0), f"frame {i}"
+
+
+def test_errors_like_reference_panics(fb):
+    with pytest.raises(fb.FloError):
+        fb.Encoder(44100, 0, 16).encode(np.zeros(4, np.float32), b"")
+    with pytest.raises(fb.FloError):
+        fb.Encoder(0, 1, 16).encode(np.zeros(4, np.float32), b"")
