@@ -1,0 +1,1156 @@
+// ----------------------------------------------------------------------------
+// shared state of the frame-encode CTA
+// ----------------------------------------------------------------------------
+constexpr int GROUP = 2;              // channels analysed jointly (stereo = one group)
+constexpr int NLPC = MAXORD - 4;      // LPC orders 5..12
+
+// candidate states
+constexpr int CS_ABSENT = 0, CS_EXACT = 1, CS_BOUNDED = 2;
+
+struct ChanState {
+    // layout of the coded channel (after the mid/side decision)
+    const int16_t *pa, *pb;
+    int msmode;                       // 0 plain, 1 mid = L + R, 2 side = L - R (encoder.rs:156-170)
+    int n;                            // samples in this channel
+    int nchunks;                      // ceil(n / CH)
+    int item_base;                    // first item of this channel in the flattened (channel, chunk) space
+    // pass 1: fixed-predictor statistics + autocorrelation
+    u64 fix_sum[5];
+    u32 fix_or[5];
+    i64 ac[MAXORD + 1];
+    // Levinson-Durbin results, by order - 5
+    double qd[NLPC][MAXORD];          // q / 2^shift as f64 (exact), for the FP64-pipe FIR
+    i32 qc[NLPC][MAXORD];             // quantised coefficients (lpc.rs:263-273)
+    i32 lpc_ok[NLPC];
+    i32 lpc_shift[NLPC];
+    i32 lpc_j0[NLPC];                 // guessed shift window {j0, j0 + 1} for sum(w >> j)
+    // pass 2: LPC statistics
+    u64 l_sum[NLPC];
+    u32 l_or[NLPC];
+    u64 l_t0[NLPC], l_t1[NLPC];
+    // candidates: 0 raw, 1..5 fixed 0..4, 6..13 lpc 5..12
+    i32 cand_state[NCAND];
+    i32 cand_k[NCAND];
+    i64 cand_size[NCAND];             // exact bytes when CS_EXACT
+    u64 cand_sumabs[NCAND];
+    // exact pass (pass 3)
+    i32 ex_cand;                      // candidate being evaluated this round (-1 none)
+    u64 ex_s;
+    u32 ex_max;
+};
+
+struct Smem {
+    ChanState cs[GROUP];
+    i32 wcoef[MAXORD];                // winner's coefficients while packing
+    double wqd[MAXORD];
+    u32 scan_warp[NWARP];
+    u32 scan_total;
+    u32 g;                            // current global frame
+    i32 ms;                           // mid/side chosen (encoder.rs:94-100)
+    i32 loud;
+    i32 more;                         // pass-3 rounds pending
+    u64 ms_var[3];
+    u64 frame_excl;                   // exclusive prefix of frame sizes
+    u32 ring[RING_WORDS];             // bit-packer staging ring (big-endian bit order words)
+};
+
+size_t encode_static_smem() { return sizeof(Smem); }
+
+__device__ __forceinline__ u64 warp_sum64(u64 v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
+    return v;
+}
+__device__ __forceinline__ void atomic_add64(u64 *p, u64 v) { atomicAdd(reinterpret_cast<unsigned long long *>(p), v); }
+
+// ----------------------------------------------------------------------------
+// scalar pieces of the reference
+// ----------------------------------------------------------------------------
+// f32_to_i32, core/audio_constants.rs:18-20: (x * 32767.0).clamp(-32768, 32767) as i32.
+// cvt.rzi saturates and maps NaN to 0 exactly like Rust's `as i32`; clamping the
+// truncated integer equals truncating the clamped float because both bounds are integers.
+__device__ __forceinline__ i32 f32_to_i32(float x) {
+    float y = __fmul_rn(x, 32767.0f);
+    int v = __float2int_rz(y);
+    return max(-32768, min(32767, v));
+}
+// silence test of encoder.rs:70: |x| < 1e-7 (NaN is not silent)
+__device__ __forceinline__ bool is_loud(float x) { return !(fabsf(x) < 1e-7f); }
+// reflo/src/audio.rs:247-254: s as f32 * (1.0 / 32768.0)
+__device__ __forceinline__ float pcm_to_f32(int s) { return __fmul_rn((float)s, 1.0f / 32768.0f); }
+
+template <typename T> __device__ __forceinline__ float sample_f32(const T *p, size_t i);
+template <> __device__ __forceinline__ float sample_f32<float>(const float *p, size_t i) { return __ldg(p + i); }
+template <> __device__ __forceinline__ float sample_f32<int16_t>(const int16_t *p, size_t i) { return pcm_to_f32(__ldg(p + i)); }
+
+__device__ __forceinline__ int bitlen32(u32 v) { return 32 - __clz((int)v); }
+
+// estimate_rice_parameter_i32, core/rice.rs:29-69, from OR(|r|) and sum(|r|):
+// only the bit length of max|r| enters the rule, and OR has the same bit length as the maximum.
+__device__ __forceinline__ int rice_k_or(u32 or_abs, u64 sum_abs, u32 n) {
+    if (n == 0) return 4;
+    if (or_abs == 0) return 0;
+    const int bl = bitlen32(or_abs);              // bitlen(max_abs)
+    const int min_k = bl >= 8 ? bl + 1 - 8 : 0;   // 2 max > 255  <=>  max >= 128; bits_needed = bl + 1
+    const u32 mean = (u32)(sum_abs / (u64)n);
+    const int mean_k = mean > 0 ? bitlen32(mean) : 0;
+    const int k = max(min_k, mean_k);
+    return min(k, 15);
+}
+
+// lpc_order_from_level, encoder.rs:289-302
+__device__ __forceinline__ int order_of_level(int level) {
+    const int t[10] = {0, 2, 4, 4, 6, 8, 8, 10, 12, 12};
+    return t[level < 0 ? 0 : (level > 9 ? 9 : level)];
+}
+
+// Size algebra (rice.rs:97-113): with u = zigzag(r), w = r ^ (r >> 31) = |r| - [r < 0]:
+//   u >> k == w >> (k - 1) for k >= 1, and sum(u) = sum(w) + sum(|r|).
+// So for S = sum(w >> max(k - 1, 0)):  bits = S + n (1 + k)  (k >= 1),  bits = S + sum|r| + n  (k == 0).
+// The 255 cap of rice.rs:103 never binds: k >= bitlen(2 max|r|) - 8 makes u >> k <= 255.
+__device__ __forceinline__ i64 rice_bytes(u64 S, u64 sum_abs, u32 n, int k) {
+    const u64 bits = k >= 1 ? S + (u64)n * (u64)(1 + k) : S + sum_abs + (u64)n;
+    return (i64)((bits + 7) >> 3);
+}
+// bounds on the encoded size from sum|r| and k alone: sum|r| / 2^j - n <= S <= sum|r| / 2^j, j = max(k - 1, 0)
+__device__ __forceinline__ void rice_bounds(u64 sum_abs, u32 n, int k, i64 &lb, i64 &ub) {
+    const int j = k >= 1 ? k - 1 : 0;
+    const u64 hi = sum_abs >> j;
+    const u64 c = (sum_abs + ((1ull << j) - 1)) >> j;
+    const u64 lo = c > n ? c - n : 0;
+    lb = rice_bytes(lo, sum_abs, n, k);
+    ub = rice_bytes(hi, sum_abs, n, k);
+}
+
+// levinson_durbin_int, lpc.rs:225-276 -- sequential f64, every product and sum rounded
+// separately.  The recursion is prefix consistent (the order-m result is the state after
+// iteration m-1), so one run to order P yields every order 5..P.  Also derives, per order,
+// the guessed shift window for the single-pass size evaluation from the prediction error.
+__device__ void levinson_all_orders(ChanState &cs, int P) {
+    for (int o = 0; o < NLPC; o++) { cs.lpc_ok[o] = 0; cs.lpc_shift[o] = 0; cs.lpc_j0[o] = 0; }
+    if (cs.ac[0] == 0) return;
+    double a[MAXORD], nc[MAXORD];
+    for (int i = 0; i < MAXORD; i++) a[i] = 0.0;
+    double err = (double)cs.ac[0];
+    for (int i = 0; i < P; i++) {
+        double lambda = (double)cs.ac[i + 1];
+        for (int j = 0; j < i; j++) lambda = __dsub_rn(lambda, __dmul_rn(a[j], (double)cs.ac[i - j]));
+        if (fabs(err) < 1e-10) return;
+        double gamma = __ddiv_rn(lambda, err);
+        if (fabs(gamma) >= 1.0) return;
+        nc[i] = gamma;
+        for (int j = 0; j < i; j++) nc[j] = __dsub_rn(a[j], __dmul_rn(gamma, a[i - 1 - j]));
+        for (int j = 0; j <= i; j++) a[j] = nc[j];
+        err = __dmul_rn(err, __dsub_rn(1.0, __dmul_rn(gamma, gamma)));
+        const int o = i + 1;
+        if (o >= 5) {
+            double mx = 0.0;
+            for (int j = 0; j < o; j++) { double t = fabs(a[j]); if (t == t && t > mx) mx = t; }
+            if (mx == 0.0 || isinf(mx)) continue;
+            // shift = min(floor(log2(2^30 / max)) as u8, 15); floor(log2(v)) of a positive finite
+            // double is its binary exponent (|a_j| <= C(12,6) = 924 makes this 15 in practice).
+            double v = __ddiv_rn(1073741824.0, mx);
+            int e = isinf(v) ? 255 : ilogb(v);
+            int shift = e < 0 ? 0 : (e > 15 ? 15 : e);
+            double scale = (double)(1ll << shift);
+            for (int j = 0; j < o; j++) {
+                double q = round(__dmul_rn(a[j], scale));       // f64::round: half away from zero
+                i32 qi = q >= 2147483647.0 ? 2147483647 : (q <= -2147483648.0 ? (-2147483647 - 1) : (i32)q);
+                cs.qc[o - 5][j] = qi;
+                cs.qd[o - 5][j] = ldexp((double)qi, -shift);
+            }
+            cs.lpc_shift[o - 5] = shift;
+            cs.lpc_ok[o - 5] = 1;
+            // Heuristic only (exactness never depends on it): mean|r| ~ 0.64 * rms(r), rms^2 ~ err / n.
+            // The window {j0, j0+1} must contain max(k-1, 0); a miss is re-evaluated exactly in pass 3.
+            double rms2 = err > 0.0 ? err / (double)cs.n : 0.0;
+            double lg = rms2 > 1e-30 ? 0.5 * log2(rms2) - 0.64 : -10.0;
+            int j0 = (int)floor(lg - 0.5);
+            cs.lpc_j0[o - 5] = j0 < 0 ? 0 : (j0 > 14 ? 14 : j0);
+        }
+    }
+}
+
+// ----------------------------------------------------------------------------
+// sample access: 16 samples of the coded channel starting at i0 (multiple of 16)
+// plus NH samples of history (zero before the frame start; planes are zero padded
+// behind the channel end).  x[NH + j] = s[i0 + j], x[NH - 1 - h] = s[i0 - 1 - h].
+// ----------------------------------------------------------------------------
+__device__ __forceinline__ void unpack8(const int4 v, i32 *t) {
+    t[0] = (i32)(int16_t)(v.x & 0xffff); t[1] = v.x >> 16;
+    t[2] = (i32)(int16_t)(v.y & 0xffff); t[3] = v.y >> 16;
+    t[4] = (i32)(int16_t)(v.z & 0xffff); t[5] = v.z >> 16;
+    t[6] = (i32)(int16_t)(v.w & 0xffff); t[7] = v.w >> 16;
+}
+template <int NH>
+__device__ __forceinline__ void load_plane(const int16_t *pl, int i0, i32 (&x)[NH + CH]) {
+    i32 t[32];
+    const int4 *p = reinterpret_cast<const int4 *>(pl + i0);
+    const int4 z = make_int4(0, 0, 0, 0);
+    unpack8(p[0], t + 16);
+    unpack8(p[1], t + 24);
+    if (NH > 8) unpack8(i0 > 0 ? p[-2] : z, t);
+    if (NH > 0) unpack8(i0 > 0 ? p[-1] : z, t + 8);
+#pragma unroll
+    for (int i = 0; i < NH + CH; i++) x[i] = t[16 - NH + i];
+}
+template <int NH>
+__device__ __forceinline__ void load_x(const ChanState &cs, int i0, i32 (&x)[NH + CH]) {
+    load_plane<NH>(cs.pa, i0, x);
+    const int msmode = cs.msmode;
+    if (msmode) {
+        i32 y[NH + CH];
+        load_plane<NH>(cs.pb, i0, y);
+        if (msmode == 1) {
+#pragma unroll
+            for (int i = 0; i < NH + CH; i++) x[i] = x[i] + y[i];
+        } else {
+#pragma unroll
+            for (int i = 0; i < NH + CH; i++) x[i] = x[i] - y[i];
+        }
+    }
+}
+
+// compile-time loop over LPC orders
+template <int O, int P> struct ForOrders {
+    template <class F> static __device__ __forceinline__ void run(F &&f) {
+        f(std::integral_constant<int, O>{});
+        if constexpr (O < P) ForOrders<O + 1, P>::run(f);
+    }
+};
+
+// fixed_predictor_residuals, lpc.rs:301-359: r_o[i] = o-th difference for i >= o and the
+// i-th difference for i < o.  Streams through one chunk; fn(j, r0..r4) per sample.
+template <class F>
+__device__ __forceinline__ void fixed_chunk(const i32 *x /* 4 history + CH */, bool first, F &&fn) {
+    i32 xp = x[3];
+    i32 p1 = x[3] - x[2];
+    i32 p1b = x[2] - x[1], p1c = x[1] - x[0];
+    i32 p2 = p1 - p1b, p2b = p1b - p1c;
+    i32 p3 = p2 - p2b;
+#pragma unroll
+    for (int j = 0; j < CH; j++) {
+        i32 d0 = x[4 + j];
+        i32 d1 = d0 - xp;
+        i32 d2 = d1 - p1;
+        i32 d3 = d2 - p2;
+        i32 d4 = d3 - p3;
+        xp = d0; p1 = d1; p2 = d2; p3 = d3;
+        i32 r2 = d2, r3 = d3, r4 = d4;
+        if (j < 4 && first) {              // warm-up of lpc.rs:311-352
+            if (j == 0) { d1 = d0; r2 = d0; r3 = d0; r4 = d0; }
+            if (j == 1) { r2 = d1; r3 = d1; r4 = d1; }
+            if (j == 2) { r3 = d2; r4 = d2; }
+            if (j == 3) { r4 = d3; }
+        }
+        fn(j, d0, d1, r2, r3, r4);
+    }
+}
+
+// calc_residuals_int, lpc.rs:279-298, on the FP64 pipe.  With c[t] = q[t] / 2^shift (exact) the
+// chain of fused multiply-adds holds sum(q[t] * s[i-1-t]) / 2^shift exactly (|sum q s| < 2^53),
+// so floor() of it equals the reference's arithmetic `pred >> shift`; adding 1.5 * 2^52 with
+// round-down leaves that floor, modulo 2^32, in the low word -- the `pred as i32` truncation.
+// x: H history + CH samples (ints), xd the same as doubles.
+template <int O, int H, class F>
+__device__ __forceinline__ void lpc_chunk(const i32 *x, const double *xd, bool first, const double *qd, F &&fn) {
+    double c[O];
+#pragma unroll
+    for (int t = 0; t < O; t++) c[t] = qd[t];
+#pragma unroll
+    for (int j = 0; j < CH; j++) {
+        double p = 0.0;
+#pragma unroll
+        for (int t = 0; t < O; t++) p = __fma_rn(c[t], xd[H + j - 1 - t], p);
+        const int pi = __double2loint(__dadd_rd(p, 6755399441055744.0));
+        i32 r = (i32)((u32)x[H + j] - (u32)pi);
+        if (first && j < O) r = x[H + j];            // warm-up, lpc.rs:283-285
+        fn(j, r);
+    }
+}
+
+// ----------------------------------------------------------------------------
+// flattened (channel, chunk) item loop: items of one warp iteration always belong to one
+// channel (every channel's chunk count is padded to a multiple of 32), so per-channel
+// accumulators are flushed with warp shuffles when the warp moves to the next channel.
+// ----------------------------------------------------------------------------
+template <class Reset, class Body, class Flush>
+__device__ __forceinline__ void for_items(const Smem &s, int nch, int total_items, Reset &&reset, Body &&body, Flush &&flush) {
+    int cur = -1;
+    int since = 0;                       // chunks since the last flush: 32-bit partial sums hold 2^24 per chunk
+    for (int item = threadIdx.x; item < total_items; item += NT) {
+        int c = 0;
+#pragma unroll
+        for (int q = 1; q < GROUP; q++)
+            if (q < nch && item >= s.cs[q].item_base) c = q;
+        if (c != cur || since >= 128) {
+            if (cur >= 0) flush(cur);
+            reset();
+            cur = c;
+            since = 0;
+        }
+        const int chunk = item - s.cs[c].item_base;
+        if (chunk < s.cs[c].nchunks) body(c, chunk);
+        since++;
+    }
+    if (cur >= 0) flush(cur);
+}
+
+// ---- pass 1: fixed-predictor statistics (sum|r|, OR|r|) + autocorrelation (lpc.rs:213-221) ----
+template <int P>
+__device__ void pass1(Smem &s, int nch, int total_items) {
+    constexpr int NH = P > 4 ? P : 4;
+    u32 fsum[5], forr[5];               // |r| <= 2^20 for the fixed predictors: 2^24 per chunk
+    double acc[P + 1];
+    const int lane = threadIdx.x & 31;
+    for_items(
+        s, nch, total_items,
+        [&]() {
+#pragma unroll
+            for (int o = 0; o < 5; o++) { fsum[o] = 0; forr[o] = 0; }
+#pragma unroll
+            for (int l = 0; l <= P; l++) acc[l] = 0.0;
+        },
+        [&](int c, int chunk) {
+            const ChanState &cs = s.cs[c];
+            const int i0 = chunk * CH;
+            const int nv = min(CH, cs.n - i0);
+            i32 x[NH + CH];
+            load_x<NH>(cs, i0, x);
+            if constexpr (P > 0) {
+                // exact: |x| <= 2^16, so every partial sum is an integer far below 2^53
+                double xd[NH + CH];
+#pragma unroll
+                for (int i = 0; i < NH + CH; i++) xd[i] = (double)x[i];
+#pragma unroll
+                for (int j = 0; j < CH; j++) {
+#pragma unroll
+                    for (int l = 0; l <= P; l++) acc[l] = __fma_rn(xd[NH + j], xd[NH + j - l], acc[l]);
+                }
+            }
+            fixed_chunk(x + (NH - 4), i0 == 0, [&](int j, i32 r0, i32 r1, i32 r2, i32 r3, i32 r4) {
+                if (j < nv) {
+                    const u32 a0 = (u32)abs(r0), a1 = (u32)abs(r1), a2 = (u32)abs(r2), a3 = (u32)abs(r3), a4 = (u32)abs(r4);
+                    fsum[0] += a0; fsum[1] += a1; fsum[2] += a2; fsum[3] += a3; fsum[4] += a4;
+                    forr[0] |= a0; forr[1] |= a1; forr[2] |= a2; forr[3] |= a3; forr[4] |= a4;
+                }
+            });
+        },
+        [&](int c) {
+            ChanState &cs = s.cs[c];
+#pragma unroll
+            for (int o = 0; o < 5; o++) {
+                const u64 t = warp_sum64((u64)fsum[o]);
+                const u32 r = __reduce_or_sync(0xffffffffu, forr[o]);
+                if (lane == 0) { atomic_add64(&cs.fix_sum[o], t); atomicOr(&cs.fix_or[o], r); }
+            }
+            if constexpr (P > 0) {
+#pragma unroll
+                for (int l = 0; l <= P; l++) {
+                    const u64 t = warp_sum64((u64)__double2ll_rn(acc[l]));
+                    if (lane == 0) atomic_add64(reinterpret_cast<u64 *>(&cs.ac[l]), t);
+                }
+            }
+        });
+}
+
+// ---- pass 2: LPC candidates 5..P: sum|r|, OR|r| and sum(w >> j) for the guessed window ----
+template <int P>
+__device__ void pass2(Smem &s, int nch, int total_items) {
+    constexpr int NO = P - 4;
+    // 32-bit partial sums: only candidates with OR|r| < 2^21 are ever used (after_pass2), 2^25 per chunk
+    u32 lsum[NO], lt0[NO], lt1[NO], lorr[NO];
+    const int lane = threadIdx.x & 31;
+    for_items(
+        s, nch, total_items,
+        [&]() {
+#pragma unroll
+            for (int i = 0; i < NO; i++) { lsum[i] = 0; lt0[i] = 0; lt1[i] = 0; lorr[i] = 0; }
+        },
+        [&](int c, int chunk) {
+            const ChanState &cs = s.cs[c];
+            const int i0 = chunk * CH;
+            const int nv = min(CH, cs.n - i0);
+            i32 x[P + CH];
+            load_x<P>(cs, i0, x);
+            double xd[P + CH];
+#pragma unroll
+            for (int i = 0; i < P + CH; i++) xd[i] = (double)x[i];
+            ForOrders<5, P>::run([&](auto oc) {
+                constexpr int O = decltype(oc)::value;
+                if (cs.lpc_ok[O - 5]) {
+                    const int j0 = cs.lpc_j0[O - 5];
+                    u32 sa = lsum[O - 5], t0 = lt0[O - 5], t1 = lt1[O - 5], orr = lorr[O - 5];
+                    lpc_chunk<O, P>(x, xd, i0 == 0, cs.qd[O - 5], [&](int j, i32 r) {
+                        if (j < nv) {
+                            const u32 a = (u32)abs(r);
+                            const u32 w = a + (u32)(r >> 31);          // |r| - [r < 0]
+                            sa += a; orr |= a;
+                            const u32 ws = w >> j0;
+                            t0 += ws; t1 += ws >> 1;
+                        }
+                    });
+                    lsum[O - 5] = sa; lt0[O - 5] = t0; lt1[O - 5] = t1; lorr[O - 5] = orr;
+                }
+            });
+        },
+        [&](int c) {
+            ChanState &cs = s.cs[c];
+#pragma unroll
+            for (int i = 0; i < NO; i++) {
+                const u64 a = warp_sum64((u64)lsum[i]), b = warp_sum64((u64)lt0[i]), d = warp_sum64((u64)lt1[i]);
+                const u32 r = __reduce_or_sync(0xffffffffu, lorr[i]);
+                if (lane == 0) {
+                    atomic_add64(&cs.l_sum[i], a); atomic_add64(&cs.l_t0[i], b); atomic_add64(&cs.l_t1[i], d);
+                    atomicOr(&cs.l_or[i], r);
+                }
+            }
+        });
+}
+
+// residuals of one chunk for candidate MODE (0..4 fixed, 5..12 LPC, 13 raw samples)
+template <int MODE, class F>
+__device__ __forceinline__ void cand_chunk(const ChanState &cs, int i0, const double *qd, F &&fn) {
+    if constexpr (MODE == 13) {
+        i32 x[CH];
+        load_x<0>(cs, i0, x);
+#pragma unroll
+        for (int j = 0; j < CH; j++) fn(j, x[j]);
+    } else if constexpr (MODE <= 4) {
+        i32 xf[4 + CH];
+        load_x<4>(cs, i0, xf);
+        fixed_chunk(xf, i0 == 0, [&](int j, i32 r0, i32 r1, i32 r2, i32 r3, i32 r4) {
+            fn(j, MODE == 0 ? r0 : MODE == 1 ? r1 : MODE == 2 ? r2 : MODE == 3 ? r3 : r4);
+        });
+    } else {
+        constexpr int H = MODE <= 8 ? 8 : 12;
+        i32 x[H + CH];
+        load_x<H>(cs, i0, x);
+        double xd[H + CH];
+#pragma unroll
+        for (int i = 0; i < H + CH; i++) xd[i] = (double)x[i];
+        lpc_chunk<MODE, H>(x, xd, i0 == 0, qd, fn);
+    }
+}
+
+// ---- pass 3: exact max|r| and S = sum(w >> j) for one still-open candidate per channel ----
+template <int P>
+__device__ void pass3(Smem &s, int nch, int total_items) {
+    u64 S;
+    u32 mx;
+    const int lane = threadIdx.x & 31;
+    for_items(
+        s, nch, total_items, [&]() { S = 0; mx = 0; },
+        [&](int c, int chunk) {
+            const ChanState &cs = s.cs[c];
+            const int cand = cs.ex_cand;
+            if (cand < 0) return;
+            const int i0 = chunk * CH;
+            const int nv = min(CH, cs.n - i0);
+            const int k = cs.cand_k[cand];
+            const int jj = k >= 1 ? k - 1 : 0;
+            u32 acc = 0;
+            auto fn = [&](int j, i32 r) {
+                if (j < nv) {
+                    const u32 a = (u32)abs(r);
+                    mx = max(mx, a);
+                    acc += (a + (u32)(r >> 31)) >> jj;
+                }
+            };
+            const int mode = cand - 1;                 // fixed 0..4 -> 0..4, lpc 5..12 -> 5..12
+            const double *qd = mode >= 5 ? cs.qd[mode - 5] : nullptr;
+            switch (mode) {
+                case 0: cand_chunk<0>(cs, i0, qd, fn); break;
+                case 1: cand_chunk<1>(cs, i0, qd, fn); break;
+                case 2: cand_chunk<2>(cs, i0, qd, fn); break;
+                case 3: cand_chunk<3>(cs, i0, qd, fn); break;
+                case 4: cand_chunk<4>(cs, i0, qd, fn); break;
+                default:
+                    if constexpr (P > 0) {
+                        ForOrders<5, P>::run([&](auto oc) {
+                            constexpr int O = decltype(oc)::value;
+                            if (mode == O) cand_chunk<O>(cs, i0, qd, fn);
+                        });
+                    }
+                    break;
+            }
+            S += acc;
+        },
+        [&](int c) {
+            ChanState &cs = s.cs[c];
+            const u64 t = warp_sum64(S);
+            const u32 m = __reduce_max_sync(0xffffffffu, mx);
+            if (lane == 0 && cs.ex_cand >= 0) { atomic_add64(&cs.ex_s, t); atomicMax(&cs.ex_max, m); }
+        });
+}
+
+// ----------------------------------------------------------------------------
+// candidate bookkeeping (one thread per channel)
+// ----------------------------------------------------------------------------
+// after pass 1: k of every fixed candidate, raw size; then Levinson
+__device__ void after_pass1(ChanState &cs, int P, int fmax, bool lpc_on) {
+    const u32 n = (u32)cs.n;
+    for (int j = 0; j < NCAND; j++) { cs.cand_state[j] = CS_ABSENT; cs.cand_k[j] = 0; cs.cand_size[j] = -1; cs.cand_sumabs[j] = 0; }
+    cs.cand_state[0] = CS_EXACT;
+    cs.cand_size[0] = 2ll * n;                                         // encode_raw, encoder.rs:220-226
+    for (int o = 0; o <= fmax; o++) {
+        cs.cand_state[1 + o] = CS_BOUNDED;
+        cs.cand_k[1 + o] = rice_k_or(cs.fix_or[o], cs.fix_sum[o], n);
+        cs.cand_sumabs[1 + o] = cs.fix_sum[o];
+    }
+    for (int o = 0; o < NLPC; o++) cs.lpc_ok[o] = 0;
+    if (lpc_on && cs.n > 5) {
+        levinson_all_orders(cs, P);
+        for (int o = 5; o <= P; o++)
+            if (cs.n <= o) cs.lpc_ok[o - 5] = 0;                      // encoder.rs:255-257
+    }
+}
+
+// after pass 2: resolve the LPC candidates (encoder.rs:262-286)
+__device__ void after_pass2(ChanState &cs, int P) {
+    const u32 n = (u32)cs.n;
+    for (int o = 5; o <= P; o++) {
+        const int i = o - 5, c = 1 + o;
+        if (!cs.lpc_ok[i]) continue;
+        const u32 orr = cs.l_or[i];
+        const int bl = bitlen32(orr);
+        if (bl >= 21) continue;                                       // max|r| >= 2^20 > 1_000_000: rejected
+        const int k = rice_k_or(orr, cs.l_sum[i], n);
+        cs.cand_k[c] = k;
+        cs.cand_sumabs[c] = cs.l_sum[i];
+        const int jj = k >= 1 ? k - 1 : 0;
+        if (bl <= 19 && (jj == cs.lpc_j0[i] || jj == cs.lpc_j0[i] + 1)) {
+            const u64 S = jj == cs.lpc_j0[i] ? cs.l_t0[i] : cs.l_t1[i];
+            cs.cand_state[c] = CS_EXACT;
+            cs.cand_size[c] = rice_bytes(S, cs.l_sum[i], n, k);
+        } else {
+            cs.cand_state[c] = CS_BOUNDED;                            // window miss or 2^19 <= max|r| < 2^20
+        }
+    }
+}
+
+// Pick the next candidate that still needs an exact evaluation: bounded, and its lower bound
+// does not exceed the best upper bound (otherwise it can never be the strictly-smallest one).
+// Among those the one with the smallest lower bound goes first (it tightens the bound most).
+__device__ int next_open_candidate(ChanState &cs, bool prune) {
+    const u32 n = (u32)cs.n;
+    i64 best_ub = INT64_MAX;
+    for (int j = 0; j < NCAND; j++) {
+        if (cs.cand_state[j] == CS_EXACT) best_ub = min(best_ub, cs.cand_size[j]);
+        else if (cs.cand_state[j] == CS_BOUNDED) {
+            i64 lb, ub;
+            rice_bounds(cs.cand_sumabs[j], n, cs.cand_k[j], lb, ub);
+            // an LPC candidate with 2^19 <= max|r| < 2^20 may still be rejected: its upper bound does not count
+            const bool maybe_rejected = j >= 6 && bitlen32(cs.l_or[j - 6]) == 20;
+            if (!maybe_rejected) best_ub = min(best_ub, ub);
+        }
+    }
+    int pick = -1;
+    i64 pick_lb = INT64_MAX;
+    for (int j = 0; j < NCAND; j++) {
+        if (cs.cand_state[j] != CS_BOUNDED) continue;
+        i64 lb, ub;
+        rice_bounds(cs.cand_sumabs[j], n, cs.cand_k[j], lb, ub);
+        if (prune && lb > best_ub) { cs.cand_state[j] = CS_ABSENT; continue; }   // provably not the winner
+        if (lb < pick_lb) { pick_lb = lb; pick = j; }
+    }
+    return pick;
+}
+
+__device__ void after_pass3(ChanState &cs) {
+    const int c = cs.ex_cand;
+    if (c < 0) return;
+    const u32 n = (u32)cs.n;
+    if (c >= 6 && cs.ex_max > 1000000u) { cs.cand_state[c] = CS_ABSENT; return; }   // encoder.rs:269-272
+    cs.cand_state[c] = CS_EXACT;
+    cs.cand_size[c] = rice_bytes(cs.ex_s, cs.cand_sumabs[c], n, cs.cand_k[c]);
+}
+
+// ----------------------------------------------------------------------------
+// bit packer
+// ----------------------------------------------------------------------------
+// Codes of one chunk for the winner: zigzag(r) (rice.rs:96), or the two little-endian bytes of
+// the sample as one 16-bit MSB-first code for a raw channel ((s as i16).to_le_bytes(), encoder.rs:222-224).
+template <int MODE>
+__device__ __forceinline__ void chunk_codes(const ChanState &cs, int i0, const double *qd, u32 (&u)[CH]) {
+    cand_chunk<MODE>(cs, i0, qd, [&](int j, i32 r) {
+        if constexpr (MODE == 13) {
+            const u32 v = (u32)r & 0xffffu;
+            u[j] = ((v & 0xff) << 8) | (v >> 8);
+        } else {
+            u[j] = ((u32)r << 1) ^ (u32)(r >> 31);
+        }
+    });
+}
+
+template <bool WINDOWED>
+__device__ __forceinline__ void emit_chunk(u32 *ring, const u32 (&u)[CH], int nv, int k, bool raw, u64 start,
+                                           u32 wlo, u32 whi) {
+    u32 w = (u32)(start >> 5);
+    int nb = (int)(start & 31);
+    u64 acc = 0;
+    bool firstw = true;
+    auto out = [&](u32 word) {
+        if (!WINDOWED || (w >= wlo && w < whi)) {
+            if (firstw) atomicOr(&ring[w & (RING_WORDS - 1)], word);
+            else ring[w & (RING_WORDS - 1)] = word;
+        }
+        firstw = false;
+        w++;
+    };
+    auto put = [&](u32 v, int len) {
+        acc = (acc << len) | v;
+        nb += len;
+        if (nb >= 32) { out((u32)(acc >> (nb - 32))); nb -= 32; }
+    };
+#pragma unroll
+    for (int j = 0; j < CH; j++) {
+        if (j < nv) {
+            if (raw) {
+                put(u[j], 16);
+            } else {                               // encode_sample, rice.rs:94-114
+                u32 q = u[j] >> k;
+                u32 rem = u[j] & ((1u << k) - 1u);
+                if (q <= 16) {
+                    put((((1u << q) - 1u) << (k + 1)) | rem, (int)q + k + 1);
+                } else {
+                    while (q > 0) { u32 t = q < 24 ? q : 24; put((1u << t) - 1u, (int)t); q -= t; }
+                    put(rem, k + 1);
+                }
+            }
+        }
+    }
+    if (nb > 0) {
+        u32 word = (u32)(acc << (32 - nb));
+        if (!WINDOWED || (w >= wlo && w < whi)) atomicOr(&ring[w & (RING_WORDS - 1)], word);
+    }
+}
+
+// Copy completed ring words [wa, wb) to the output and clear them.  Word w of the ring maps
+// to the 4-byte aligned address abase + 4 w; only bytes inside [lo, hi) belong to this payload.
+__device__ __forceinline__ void flush_ring(u32 *ring, uint8_t *obase, u64 abase, u64 lo, u64 hi, u32 wa, u32 wb) {
+    for (u32 w = wa + threadIdx.x; w < wb; w += NT) {
+        const u32 slot = w & (RING_WORDS - 1);
+        const u32 v = ring[slot];
+        ring[slot] = 0;
+        const u64 a = abase + 4ull * w;
+        if (a >= lo && a + 4 <= hi) {
+            *reinterpret_cast<u32 *>(obase + a) = __byte_perm(v, 0, 0x0123);
+        } else {
+#pragma unroll
+            for (int b = 0; b < 4; b++)
+                if (a + b >= lo && a + b < hi) obase[a + b] = (uint8_t)(v >> (24 - 8 * b));
+        }
+    }
+}
+
+// Pack one channel's residual payload at byte offset `pos` (relative to obase, which is 4-byte
+// aligned) -- encode_i32 / BitWriter (rice.rs:84-92, 162-208) or encode_raw (encoder.rs:220-226).
+template <int P>
+__device__ void pack_channel(Smem &s, const ChanState &cs, const ChanResult &cr, uint8_t *obase, u64 pos, u32 *err) {
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    const int n = cs.n;
+    const int mode = cr.kind == 0 ? 13 : cr.order;
+    const bool raw = cr.kind == 0;
+    const int k = cr.k;
+    const u64 abase = pos & ~3ull;
+    const u64 lo = pos, hi = pos + cr.nbytes;
+    u64 bitpos = (pos & 3ull) * 8ull;
+    u32 wfl = 0;
+    const int per_sc = NT * CH;
+    const int nsc = (n + per_sc - 1) / per_sc;
+    const double *qd = s.wqd;
+    for (int sc = 0; sc < nsc; sc++) {
+        const int i0 = sc * per_sc + tid * CH;
+        const int nv = max(0, min(CH, n - i0));
+        u32 u[CH];
+        u32 tb = 0;
+        if (nv > 0) {
+            switch (mode) {
+                case 0: chunk_codes<0>(cs, i0, qd, u); break;
+                case 1: chunk_codes<1>(cs, i0, qd, u); break;
+                case 2: chunk_codes<2>(cs, i0, qd, u); break;
+                case 3: chunk_codes<3>(cs, i0, qd, u); break;
+                case 4: chunk_codes<4>(cs, i0, qd, u); break;
+                case 13: chunk_codes<13>(cs, i0, qd, u); break;
+                default:
+                    if constexpr (P > 0) {
+                        ForOrders<5, P>::run([&](auto oc) {
+                            constexpr int O = decltype(oc)::value;
+                            if (mode == O) chunk_codes<O>(cs, i0, qd, u);
+                        });
+                    }
+                    break;
+            }
+            if (raw) {
+                tb = 16u * (u32)nv;
+            } else {
+#pragma unroll
+                for (int j = 0; j < CH; j++)
+                    if (j < nv) tb += (u[j] >> k) + 1u + (u32)k;
+            }
+        }
+        // block exclusive scan of the chunk bit counts
+        u32 inc = tb;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            u32 t = __shfl_up_sync(0xffffffffu, inc, o);
+            if (lane >= o) inc += t;
+        }
+        if (lane == 31) s.scan_warp[wid] = inc;
+        __syncthreads();
+        if (wid == 0) {
+            u32 v = lane < NWARP ? s.scan_warp[lane] : 0;
+            u32 vi = v;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                u32 t = __shfl_up_sync(0xffffffffu, vi, o);
+                if (lane >= o) vi += t;
+            }
+            if (lane < NWARP) s.scan_warp[lane] = vi - v;
+            if (lane == NWARP - 1) s.scan_total = vi;
+        }
+        __syncthreads();
+        const u64 start = bitpos + s.scan_warp[wid] + (inc - tb);
+        const u64 end_sc = bitpos + s.scan_total;
+        const u32 wlast = (u32)((end_sc + 31) >> 5);
+        u32 wlo = wfl;
+        if (wlast - wlo <= (u32)RING_WORDS) {
+            // common case: the whole super-chunk fits the staging ring
+            if (nv > 0) emit_chunk<false>(s.ring, u, nv, k, raw, start, 0, 0);
+            __syncthreads();
+            const u32 wend = (u32)(end_sc >> 5);
+            flush_ring(s.ring, obase, abase, lo, hi, wlo, wend);
+            __syncthreads();
+            wlo = wend;
+        } else {
+            for (;;) {
+                const u32 whi = wlo + RING_WORDS;
+                if (nv > 0) emit_chunk<true>(s.ring, u, nv, k, raw, start, wlo, whi);
+                __syncthreads();
+                const u32 wend = min(whi, (u32)(end_sc >> 5));
+                flush_ring(s.ring, obase, abase, lo, hi, wlo, wend);
+                __syncthreads();
+                wlo = wend;
+                if (whi >= wlast) break;
+            }
+        }
+        wfl = wlo;
+        bitpos = end_sc;
+    }
+    if (bitpos & 31) flush_ring(s.ring, obase, abase, lo, hi, wfl, wfl + 1);
+    if (tid == 0) {
+        const u64 bits = bitpos - (pos & 3ull) * 8ull;
+        if (((bits + 7) >> 3) != (u64)cr.nbytes) atomicExch(err, 0xBAD00001u);
+    }
+    __syncthreads();
+}
+
+// ----------------------------------------------------------------------------
+// decoupled look-back: exclusive prefix of frame sizes in global frame order
+// ----------------------------------------------------------------------------
+constexpr u64 ST_AGG = 1ull << 62, ST_PRE = 2ull << 62, ST_MASK = (1ull << 62) - 1;
+
+__device__ __forceinline__ u64 ld_status(const u64 *p) {
+    u64 v;
+    asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_status(u64 *p, u64 v) {
+    asm volatile("st.relaxed.gpu.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+
+// called by warp 0; returns the exclusive prefix in every lane
+__device__ u64 lookback_exclusive(u64 *status, u32 g, u64 mine) {
+    const int lane = threadIdx.x & 31;
+    if (g == 0) {
+        if (lane == 0) st_status(status, ST_PRE | mine);
+        return 0;
+    }
+    if (lane == 0) st_status(status + g, ST_AGG | mine);
+    u64 excl = 0;
+    i64 idx = (i64)g - 1;
+    for (;;) {
+        const i64 j = idx - lane;
+        u64 v = ST_PRE;                       // virtual predecessor before frame 0: prefix 0
+        if (j >= 0) {
+            do { v = ld_status(status + j); } while ((v >> 62) == 0);
+        }
+        const u32 pm = __ballot_sync(0xffffffffu, (v >> 62) == 2);
+        u64 val = v & ST_MASK;
+        if (pm) {
+            const int first = __ffs(pm) - 1;  // nearest predecessor holding an inclusive prefix
+            if (lane > first) val = 0;
+            val = warp_sum64(val);
+            excl += __shfl_sync(0xffffffffu, val, 0);
+            break;
+        }
+        val = warp_sum64(val);
+        excl += __shfl_sync(0xffffffffu, val, 0);
+        idx -= 32;
+    }
+    if (lane == 0) st_status(status + g, ST_PRE | (excl + mine));
+    return excl;
+}
+
+// ----------------------------------------------------------------------------
+// ingest: quantise, silence test, deinterleave into 16-bit planes, mid/side energies
+// ----------------------------------------------------------------------------
+// channel header bytes inside an ALPC frame, writer.rs:272-299 (none in a Raw-typed frame, :267-270)
+__device__ __forceinline__ u32 chan_hdr_bytes(bool all_raw, const ChanResult &r) {
+    if (all_raw) return 0;
+    return 1u + 4u * (r.kind == 2 ? (u32)r.order : 0u) + 1u + 1u + (r.kind != 0 ? 1u : 0u);
+}
+__device__ __forceinline__ void put_u32le(uint8_t *p, u32 v) {
+    p[0] = (uint8_t)v; p[1] = (uint8_t)(v >> 8); p[2] = (uint8_t)(v >> 16); p[3] = (uint8_t)(v >> 24);
+}
+__device__ __forceinline__ u32 pack2(i32 a, i32 b) { return ((u32)a & 0xffffu) | ((u32)b << 16); }
+
+struct IngestAcc {
+    bool loud = false;
+    i64 vl = 0, vr = 0, vs = 0;
+    __device__ __forceinline__ void pair(float a, float b, i32 &l, i32 &r) {
+        loud |= is_loud(a) | is_loud(b);
+        l = f32_to_i32(a); r = f32_to_i32(b);
+        const i32 sd = l - r;
+        vl += (i64)l * l; vr += (i64)r * r; vs += (i64)sd * sd;     // encoder.rs:136-149
+    }
+};
+
+template <typename T>
+__device__ void ingest_frame(Smem &s, const T *in, u32 len, u32 C, int16_t *planes, u32 stride) {
+    const int tid = threadIdx.x;
+    IngestAcc A;
+    if (C == 2) {
+        const u32 nf = len >> 1;
+        u32 done = 0;
+        // vector path: 8 sample-frames per thread step, 16-byte loads, 16-byte plane stores
+        if ((reinterpret_cast<uintptr_t>(in) & 15) == 0) {
+            const u32 ngrp = nf >> 3;
+            for (u32 gI = tid; gI < ngrp; gI += NT) {
+                float f[16];
+                if constexpr (sizeof(T) == 4) {
+                    const float4 *p = reinterpret_cast<const float4 *>(in) + (size_t)gI * 4;
+                    const float4 a = __ldg(p), b = __ldg(p + 1), c = __ldg(p + 2), d = __ldg(p + 3);
+                    f[0] = a.x; f[1] = a.y; f[2] = a.z; f[3] = a.w; f[4] = b.x; f[5] = b.y; f[6] = b.z; f[7] = b.w;
+                    f[8] = c.x; f[9] = c.y; f[10] = c.z; f[11] = c.w; f[12] = d.x; f[13] = d.y; f[14] = d.z; f[15] = d.w;
+                } else {
+                    const int4 *p = reinterpret_cast<const int4 *>(in) + (size_t)gI * 2;
+                    const int4 a = __ldg(p), b = __ldg(p + 1);
+                    const int wv[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+#pragma unroll
+                    for (int i = 0; i < 8; i++) {
+                        f[2 * i] = pcm_to_f32((int)(int16_t)(wv[i] & 0xffff));
+                        f[2 * i + 1] = pcm_to_f32(wv[i] >> 16);
+                    }
+                }
+                i32 l[8], r[8];
+#pragma unroll
+                for (int i = 0; i < 8; i++) A.pair(f[2 * i], f[2 * i + 1], l[i], r[i]);
+                *reinterpret_cast<uint4 *>(planes + (size_t)gI * 8) =
+                    make_uint4(pack2(l[0], l[1]), pack2(l[2], l[3]), pack2(l[4], l[5]), pack2(l[6], l[7]));
+                *reinterpret_cast<uint4 *>(planes + stride + (size_t)gI * 8) =
+                    make_uint4(pack2(r[0], r[1]), pack2(r[2], r[3]), pack2(r[4], r[5]), pack2(r[6], r[7]));
+            }
+            done = ngrp << 3;
+        }
+        for (u32 i = done + tid; i < nf; i += NT) {
+            i32 l, r;
+            A.pair(sample_f32<T>(in, 2 * (size_t)i), sample_f32<T>(in, 2 * (size_t)i + 1), l, r);
+            planes[i] = (int16_t)l;
+            planes[stride + i] = (int16_t)r;
+        }
+        if ((len & 1) && tid == 0) {           // ragged tail: channel 0 gets one more sample (encoder.rs:84-90)
+            const float a = sample_f32<T>(in, (size_t)len - 1);
+            A.loud |= is_loud(a);
+            planes[nf] = (int16_t)f32_to_i32(a);
+        }
+    } else if (C == 1) {
+        u32 done = 0;
+        if ((reinterpret_cast<uintptr_t>(in) & 15) == 0) {
+            const u32 ngrp = len >> 3;
+            for (u32 gI = tid; gI < ngrp; gI += NT) {
+                float f[8];
+                if constexpr (sizeof(T) == 4) {
+                    const float4 *p = reinterpret_cast<const float4 *>(in) + (size_t)gI * 2;
+                    const float4 a = __ldg(p), b = __ldg(p + 1);
+                    f[0] = a.x; f[1] = a.y; f[2] = a.z; f[3] = a.w; f[4] = b.x; f[5] = b.y; f[6] = b.z; f[7] = b.w;
+                } else {
+                    const int4 a = __ldg(reinterpret_cast<const int4 *>(in) + gI);
+                    const int wv[4] = {a.x, a.y, a.z, a.w};
+#pragma unroll
+                    for (int i = 0; i < 4; i++) {
+                        f[2 * i] = pcm_to_f32((int)(int16_t)(wv[i] & 0xffff));
+                        f[2 * i + 1] = pcm_to_f32(wv[i] >> 16);
+                    }
+                }
+                i32 v[8];
+#pragma unroll
+                for (int i = 0; i < 8; i++) { A.loud |= is_loud(f[i]); v[i] = f32_to_i32(f[i]); }
+                *reinterpret_cast<uint4 *>(planes + (size_t)gI * 8) =
+                    make_uint4(pack2(v[0], v[1]), pack2(v[2], v[3]), pack2(v[4], v[5]), pack2(v[6], v[7]));
+            }
+            done = ngrp << 3;
+        }
+        for (u32 i = done + tid; i < len; i += NT) {
+            const float a = sample_f32<T>(in, i);
+            A.loud |= is_loud(a);
+            planes[i] = (int16_t)f32_to_i32(a);
+        }
+    } else {
+        for (u32 e = tid; e < len; e += NT) {
+            const float a = sample_f32<T>(in, e);
+            A.loud |= is_loud(a);
+            const u32 c = e % C, i = e / C;
+            planes[(size_t)c * stride + i] = (int16_t)f32_to_i32(a);
+        }
+    }
+    // zero the padding behind each channel (chunk loads read up to the next multiple of 16)
+    for (u32 c = 0; c < C; c++) {
+        const u32 cl = len > c ? (len - c + C - 1) / C : 0;
+        for (u32 i = cl + tid; i < stride; i += NT) planes[(size_t)c * stride + i] = 0;
+    }
+    // block-wide: loud flag and the three energies
+    const int lane = tid & 31;
+    const u32 anyloud = __ballot_sync(0xffffffffu, A.loud);
+    if (C == 2) {
+        const u64 a = warp_sum64((u64)A.vl), b = warp_sum64((u64)A.vr), c = warp_sum64((u64)A.vs);
+        if (lane == 0) { atomic_add64(&s.ms_var[0], a); atomic_add64(&s.ms_var[1], b); atomic_add64(&s.ms_var[2], c); }
+    }
+    if (lane == 0 && anyloud) atomicOr(reinterpret_cast<u32 *>(&s.loud), 1u);
+}
+
+// ----------------------------------------------------------------------------
+// the frame-encode kernel
+// ----------------------------------------------------------------------------
+extern __shared__ __align__(16) unsigned char dyn_smem[];
+
+template <int P>
+__global__ void __launch_bounds__(NT, 1) k_encode_frames(const EncodeParams p) {
+    Smem &s = *reinterpret_cast<Smem *>(dyn_smem);
+    int16_t *smem_planes = reinterpret_cast<int16_t *>(dyn_smem + ((sizeof(Smem) + 15) & ~size_t(15)));
+    const int tid = threadIdx.x;
+    for (int i = tid; i < RING_WORDS; i += NT) s.ring[i] = 0;
+    ChanResult *cres = p.cres + (size_t)blockIdx.x * 256;
+    const int level = p.level;
+    // P = LPC max order analysed by this instantiation (0: levels 0-3, fixed predictors only)
+    const int PL = order_of_level(level);            // encoder.rs:289-302
+    const int fmax = PL < 4 ? PL : 4;
+    const bool lpc_on = P > 0;                        // level >= 3 && max_order > 4, encoder.rs:204
+    const bool prune = p.report == nullptr;      // the parity report wants every candidate's exact size
+
+    for (;;) {
+        __syncthreads();
+        if (tid == 0) {
+            s.g = atomicAdd(p.ticket, 1u);
+            s.loud = 0; s.ms = 0;
+            s.ms_var[0] = s.ms_var[1] = s.ms_var[2] = 0;
+        }
+        __syncthreads();
+        const u32 g = s.g;
+        if (g >= p.n_frames) break;
+        const uint2 fd = p.frames[g];
+        const TrackDev tr = p.tracks[fd.x];
+        const u32 C = tr.channels;
+        const u64 spf_inter = (u64)tr.sample_rate * C;                     // encoder.rs:33, 53-58
+        const u64 start = (u64)fd.y * spf_inter;
+        const u64 end = min(start + spf_inter, tr.n_inter);
+        const u32 len = (u32)(end - start);
+        const u32 frame_samples = len / C;                                 // encoder.rs:67
+        const u32 cl0 = (len + C - 1) / C;
+        const u32 stride = (cl0 + 15u) & ~15u;
+        int16_t *planes = ((u64)C * stride * 2 <= p.smem_plane_bytes)
+                              ? smem_planes
+                              : p.plane_scratch + (size_t)blockIdx.x * p.plane_scratch_elems;
+
+        if (p.format == FLO_FMT_PCM16)
+            ingest_frame<int16_t>(s, reinterpret_cast<const int16_t *>(tr.samples) + start, len, C, planes, stride);
+        else
+            ingest_frame<float>(s, reinterpret_cast<const float *>(tr.samples) + start, len, C, planes, stride);
+        __syncthreads();
+
+        const u64 data_base = tr.static_off + FILE_HDR + 4ull + 20ull * tr.n_frames;   // writer.rs:51, 89-95
+
+        if (!s.loud) {
+            // Frame::silence, encoder.rs:70-76 / types.rs:221-229: type 0, C empty channels
+            const u32 fsize = 6 + 4 * C;
+            if (tid < 32) {
+                u64 ex = lookback_exclusive(p.status, g, fsize);
+                if (tid == 0) { s.frame_excl = ex; p.frame_excl[g] = ex; p.frame_size[g] = fsize; }
+            }
+            __syncthreads();
+            uint8_t *o = p.out + data_base + s.frame_excl;
+            if (tid == 0) { o[0] = 0; put_u32le(o + 1, frame_samples); o[5] = 0; }
+            for (u32 i = tid; i < 4 * C; i += NT) o[6 + i] = 0;
+            if (p.report) {
+                for (u32 i = tid; i < REPORT_CH * NCAND; i += NT) {
+                    flo_cand_report *r = p.report + (size_t)g * REPORT_CH * NCAND + i;
+                    r->k = 0; r->pad = 0; r->size = -1;
+                }
+            }
+            continue;
+        }
+
+        // mid/side decision, encoder.rs:94-100, 131-153
+        int ms = 0;
+        if (C == 2) {
+            const i64 vl = (i64)s.ms_var[0], vr = (i64)s.ms_var[1], vs = (i64)s.ms_var[2];
+            ms = vs < (vl + vr) / 2 ? 1 : 0;
+            if (ms && (len & 1)) {             // the unpaired tail sample of L is dropped by the zip (encoder.rs:160)
+                if (tid == 0) planes[len >> 1] = 0;
+            }
+        }
+
+        // per-channel predictor search, GROUP channels at a time
+        for (u32 c0 = 0; c0 < C; c0 += GROUP) {
+            const int nch = (int)min((u32)GROUP, C - c0);
+            __syncthreads();
+            if (tid < nch) {
+                ChanState &cs = s.cs[tid];
+                const u32 c = c0 + tid;
+                u32 cl = len > c ? (len - c + C - 1) / C : 0;
+                if (ms) cl = len >> 1;                                      // zip in to_mid_side truncates, encoder.rs:160-167
+                cs.n = (int)cl;
+                cs.nchunks = (int)((cl + CH - 1) / CH);
+                cs.msmode = ms ? (c == 0 ? 1 : 2) : 0;
+                cs.pa = ms ? planes : planes + (size_t)c * stride;
+                cs.pb = planes + stride;
+                for (int o = 0; o < 5; o++) { cs.fix_sum[o] = 0; cs.fix_or[o] = 0; }
+                for (int l = 0; l <= MAXORD; l++) cs.ac[l] = 0;
+                for (int o = 0; o < NLPC; o++) { cs.l_sum[o] = 0; cs.l_or[o] = 0; cs.l_t0[o] = 0; cs.l_t1[o] = 0; cs.lpc_ok[o] = 0; }
+                cs.ex_cand = -1; cs.ex_s = 0; cs.ex_max = 0;
+            }
+            __syncthreads();
+            if (tid == 0) {
+                int base = 0;
+                for (int q = 0; q < nch; q++) { s.cs[q].item_base = base; base += (s.cs[q].nchunks + 31) & ~31; }
+                s.scan_total = (u32)base;
+            }
+            __syncthreads();
+            const int total_items = (int)s.scan_total;
+            bool any_lpc = false;
+            for (int q = 0; q < nch; q++) any_lpc |= lpc_on && s.cs[q].n > 5;
+            if (any_lpc) pass1<P>(s, nch, total_items);
+            else pass1<0>(s, nch, total_items);
+            __syncthreads();
+            if (tid < nch && s.cs[tid].n > 0) after_pass1(s.cs[tid], P, fmax, lpc_on);
+            __syncthreads();
+            bool run2 = false;
+            for (int q = 0; q < nch; q++)
+                for (int o = 0; o < NLPC; o++) run2 |= s.cs[q].n > 0 && s.cs[q].lpc_ok[o] != 0;
+            if (run2) {
+                if constexpr (P > 0) pass2<P>(s, nch, total_items);
+                __syncthreads();
+                if (tid < nch && s.cs[tid].n > 0) after_pass2(s.cs[tid], P);
+            }
+            // exact evaluation of whatever is still open (bounded candidates that can still win)
+            for (;;) {
+                __syncthreads();
+                if (tid == 0) s.more = 0;
+                __syncthreads();
+                if (tid < nch && s.cs[tid].n > 0) {
+                    ChanState &cs = s.cs[tid];
+                    cs.ex_cand = next_open_candidate(cs, prune);
+                    cs.ex_s = 0; cs.ex_max = 0;
+                    if (cs.ex_cand >= 0) atomicOr(reinterpret_cast<u32 *>(&s.more), 1u);
+                }
+                __syncthreads();
+                if (!s.more) break;
+                pass3<P>(s, nch, total_items);
+                __syncthreads();
+                if (tid < nch && s.cs[tid].n > 0) after_pass3(s.cs[tid]);
+            }
+            // encode_channel_int, encoder.rs:184-216: strictly smaller wins, candidates in order
+            if (tid < nch) {
+                ChanState &cs = s.cs[tid];
+                const u32 c = c0 + tid;
+                ChanResult r;
+                if (cs.n == 0) {
+                    r.kind = 3; r.order = 0; r.k = 0; r.nbytes = 0; r.shift = 0;
+                    for (int j = 0; j < MAXORD; j++) r.coef[j] = 0;
+                } else {
+                    i64 best = cs.cand_size[0];
+                    int bj = 0;
+                    for (int j = 1; j < NCAND; j++) {
+                        if (cs.cand_state[j] != CS_EXACT) continue;
+                        const i64 sz = cs.cand_size[j];
+                        if (sz < best) { best = sz; bj = j; }
+                    }
+                    r.kind = bj == 0 ? 0 : (bj <= 5 ? 1 : 2);
+                    r.order = bj == 0 ? 0 : bj - 1;
+                    r.k = cs.cand_k[bj];
+                    r.nbytes = (u32)best;
+                    for (int j = 0; j < MAXORD; j++) r.coef[j] = (r.kind == 2 && j < r.order) ? cs.qc[r.order - 5][j] : 0;
+                    r.shift = r.kind == 2 ? cs.lpc_shift[r.order - 5] : 0;
+                }
+                r.pad[0] = r.pad[1] = r.pad[2] = 0;
+                cres[c] = r;
+                if (p.report && c < REPORT_CH) {
+                    flo_cand_report *rep = p.report + ((size_t)g * REPORT_CH + c) * NCAND;
+                    for (int j = 0; j < NCAND; j++) {
+                        const bool ex = cs.n > 0 && cs.cand_state[j] == CS_EXACT;
+                        rep[j].k = ex ? cs.cand_k[j] : 0; rep[j].pad = 0; rep[j].size = ex ? cs.cand_size[j] : -1;
+                    }
+                }
+            }
+        }
+        __syncthreads();
+
+        // frame typing and size, encoder.rs:102-127, types.rs:242-267
+        bool all_raw = true;
+        u32 fsize = 6;
+        const u32 frame_type_alpc = (PL >= 1 && PL <= 12) ? (u32)PL : 8u;     // FrameType::from_order, types.rs:69-85
+        for (u32 c = 0; c < C; c++)
+            if (cres[c].order > 0) all_raw = false;
+        for (u32 c = 0; c < C; c++) {
+            const ChanResult &r = cres[c];
+            fsize += 4 + chan_hdr_bytes(all_raw, r) + r.nbytes;
+        }
+        if (tid < 32) {
+            u64 ex = lookback_exclusive(p.status, g, fsize);
+            if (tid == 0) { s.frame_excl = ex; p.frame_excl[g] = ex; p.frame_size[g] = fsize; }
+        }
+        __syncthreads();
+
+        // write the frame, writer.rs:236-301
+        const u64 fpos = data_base + s.frame_excl;
+        uint8_t *o = p.out;
+        if (tid == 0) {
+            o[fpos] = (uint8_t)(all_raw ? 254u : frame_type_alpc);
+            put_u32le(o + fpos + 1, frame_samples);
+            o[fpos + 5] = (uint8_t)(ms ? 1 : 0);
+        }
+        u64 pos = fpos + 6;
+        for (u32 c = 0; c < C; c++) {
+            const ChanResult r = cres[c];
+            const u32 hdr = chan_hdr_bytes(all_raw, r);
+            __syncthreads();
+            if (tid == 0) {
+                ChanState &cs = s.cs[0];
+                u32 cl = len > c ? (len - c + C - 1) / C : 0;
+                if (ms) cl = len >> 1;
+                cs.n = (int)cl;
+                cs.msmode = ms ? (c == 0 ? 1 : 2) : 0;
+                cs.pa = ms ? planes : planes + (size_t)c * stride;
+                cs.pb = planes + stride;
+            }
+            if (tid < MAXORD) { s.wcoef[tid] = r.coef[tid]; s.wqd[tid] = ldexp((double)r.coef[tid], -r.shift); }
+            __syncthreads();
+            if (tid == 0) {
+                put_u32le(o + pos, hdr + r.nbytes);
+                if (!all_raw) {
+                    uint8_t *h = o + pos + 4;
+                    const u32 nco = r.kind == 2 ? (u32)r.order : 0u;
+                    *h++ = (uint8_t)nco;
+                    for (u32 j = 0; j < nco; j++) { put_u32le(h, (u32)r.coef[j]); h += 4; }
+                    *h++ = (uint8_t)(r.kind == 2 ? r.shift : (r.kind == 1 ? 128 + r.order : 0));   // encoder.rs:243, 279
+                    *h++ = (uint8_t)(r.kind == 0 ? 2 : 0);                                         // ResidualEncoding
+                    if (r.kind != 0) *h++ = (uint8_t)r.k;
+                }
+            }
+            if (r.kind != 3 && r.nbytes > 0) pack_channel<P>(s, s.cs[0], r, o, pos + 4 + hdr, p.err);
+            pos += 4 + hdr + r.nbytes;
+        }
+        if (tid == 0 && pos - fpos != fsize) atomicExch(p.err, 0xBAD00002u);
+    }
+}
