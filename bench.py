@@ -232,6 +232,7 @@ def main() -> int:
     ev1.record()
     sync_all()
     clocks = sampler.stop() if rank == 0 else None
+    counters = ctx.last_counters()
     ms_total = ev0.elapsed_time(ev1)
     tmax = torch.tensor([ms_total], dtype=torch.float64, device=dev)
     if world > 1:
@@ -291,7 +292,7 @@ def main() -> int:
                 "pct_of_hbm_peak": 100.0 * achieved / peak, "flo_bytes_per_step_per_gpu": out_bytes,
                 "compression_ratio": 2.0 * total_inter / out_bytes, "roofline": roofline, "cpu_baseline": cpu,
                 "e2e": e2e, "gpu_launches": launches, "clocks": clocks,
-                "device_ms_per_step": sum(dev_ms) / len(dev_ms)}
+                "device_ms_per_step": sum(dev_ms) / len(dev_ms), "analysis_counters_last_step": counters}
         print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()

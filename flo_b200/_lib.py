@@ -32,7 +32,7 @@ class CandReport(C.Structure):
 EXPORTS = [
     "flo_ctx_create", "flo_ctx_destroy", "flo_encode", "flo_encode_pcm16", "flo_encode_batch",
     "flo_encode_batch_device", "flo_output_bound", "flo_ctx_set_stream", "flo_ctx_last_timing",
-    "flo_ctx_enable_report", "flo_ctx_read_report", "flo_host_alloc", "flo_host_free", "flo_free",
+    "flo_ctx_last_counters", "flo_ctx_enable_report", "flo_ctx_read_report", "flo_host_alloc", "flo_host_free", "flo_free",
     "flo_last_error", "flo_version", "flo_device_count",
 ]
 
@@ -67,6 +67,8 @@ def lib() -> C.CDLL:
     L.flo_ctx_set_stream.argtypes = [vp, vp]
     L.flo_ctx_last_timing.restype = C.c_int
     L.flo_ctx_last_timing.argtypes = [vp, C.POINTER(C.c_float), C.POINTER(u32)]
+    L.flo_ctx_last_counters.restype = C.c_int
+    L.flo_ctx_last_counters.argtypes = [vp, u64p]
     L.flo_ctx_enable_report.restype = C.c_int
     L.flo_ctx_enable_report.argtypes = [vp, C.c_int]
     L.flo_ctx_read_report.restype = C.c_int

@@ -12,8 +12,8 @@ struct ChanState {
     const int16_t *pa, *pb;
     int msmode;                       // 0 plain, 1 mid = L + R, 2 side = L - R (encoder.rs:156-170)
     int n;                            // samples in this channel
-    int nchunks;                      // ceil(n / CH)
-    int item_base;                    // first item of this channel in the flattened (channel, chunk) space
+    int nfull;                        // full chunks: n / CH
+    int tail;                         // n % CH samples in the partial tail chunk
     // pass 1: fixed-predictor statistics + autocorrelation
     u64 fix_sum[5];
     u32 fix_or[5];
@@ -247,64 +247,104 @@ __device__ __forceinline__ void fixed_chunk(const i32 *x /* 4 history + CH */, b
     }
 }
 
+// int -> f64 on the conversion pipe.  `volatile` pins each conversion where it is written, so the
+// compiler neither keeps a whole chunk of doubles alive (spills) nor re-converts a sample per use.
+__device__ __forceinline__ double cvt_f64(i32 x) {
+    double d;
+    asm volatile("cvt.rn.f64.s32 %0, %1;" : "=d"(d) : "r"(x));
+    return d;
+}
+
 // calc_residuals_int, lpc.rs:279-298, on the FP64 pipe.  With c[t] = q[t] / 2^shift (exact) the
 // chain of fused multiply-adds holds sum(q[t] * s[i-1-t]) / 2^shift exactly (|sum q s| < 2^53),
 // so floor() of it equals the reference's arithmetic `pred >> shift`; adding 1.5 * 2^52 with
 // round-down leaves that floor, modulo 2^32, in the low word -- the `pred as i32` truncation.
-// x: H history + CH samples (ints), xd the same as doubles.
+// x: H history + CH samples.  Only a sliding window of O converted samples is alive at a time.
 template <int O, int H, class F>
-__device__ __forceinline__ void lpc_chunk(const i32 *x, const double *xd, bool first, const double *qd, F &&fn) {
+__device__ __forceinline__ void lpc_chunk(const i32 *x, bool first, const double *qd, F &&fn) {
     double c[O];
 #pragma unroll
     for (int t = 0; t < O; t++) c[t] = qd[t];
+    double w[O + CH];                                  // w[i] = f64(x[H - O + i])
+#pragma unroll
+    for (int t = 0; t < O; t++) w[t] = cvt_f64(x[H - O + t]);
 #pragma unroll
     for (int j = 0; j < CH; j++) {
         double p = 0.0;
 #pragma unroll
-        for (int t = 0; t < O; t++) p = __fma_rn(c[t], xd[H + j - 1 - t], p);
+        for (int t = 0; t < O; t++) p = __fma_rn(c[t], w[O + j - 1 - t], p);
         const int pi = __double2loint(__dadd_rd(p, 6755399441055744.0));
         i32 r = (i32)((u32)x[H + j] - (u32)pi);
-        if (first && j < O) r = x[H + j];            // warm-up, lpc.rs:283-285
+        if (j < O) r = first ? x[H + j] : r;           // warm-up, lpc.rs:283-285
         fn(j, r);
+        if (j + 1 < CH) w[O + j] = cvt_f64(x[H + j]);
     }
 }
 
 // ----------------------------------------------------------------------------
-// flattened (channel, chunk) item loop: items of one warp iteration always belong to one
-// channel (every channel's chunk count is padded to a multiple of 32), so per-channel
-// accumulators are flushed with warp shuffles when the warp moves to the next channel.
+// scalar residuals at one sample index (used for the < 16 samples behind the last full chunk)
 // ----------------------------------------------------------------------------
-template <class Reset, class Body, class Flush>
-__device__ __forceinline__ void for_items(const Smem &s, int nch, int total_items, Reset &&reset, Body &&body, Flush &&flush) {
-    int cur = -1;
-    int since = 0;                       // chunks since the last flush: 32-bit partial sums hold 2^24 per chunk
-    for (int item = threadIdx.x; item < total_items; item += NT) {
-        int c = 0;
-#pragma unroll
-        for (int q = 1; q < GROUP; q++)
-            if (q < nch && item >= s.cs[q].item_base) c = q;
-        if (c != cur || since >= 128) {
-            if (cur >= 0) flush(cur);
-            reset();
-            cur = c;
-            since = 0;
-        }
-        const int chunk = item - s.cs[c].item_base;
-        if (chunk < s.cs[c].nchunks) body(c, chunk);
-        since++;
-    }
-    if (cur >= 0) flush(cur);
+__device__ __forceinline__ i32 sample_at(const ChanState &cs, int i) {
+    if (i < 0 || i >= cs.n) return 0;
+    const i32 a = cs.pa[i];
+    if (cs.msmode == 0) return a;
+    const i32 b = cs.pb[i];
+    return cs.msmode == 1 ? a + b : a - b;
+}
+// fixed_predictor_residuals (lpc.rs:301-359) at index i: the min(o, i)-th finite difference
+__device__ __noinline__ i32 fixed_residual_at(const ChanState &cs, int o, int i) {
+    const int oo = o < i ? o : i;
+    const i32 binom[5][5] = {{1, 0, 0, 0, 0}, {1, -1, 0, 0, 0}, {1, -2, 1, 0, 0}, {1, -3, 3, -1, 0}, {1, -4, 6, -4, 1}};
+    u32 r = 0;
+    for (int t = 0; t <= oo; t++) r += (u32)binom[oo][t] * (u32)sample_at(cs, i - t);
+    return (i32)r;
+}
+// calc_residuals_int (lpc.rs:279-298) at index i, in the reference's own i64 arithmetic
+__device__ __noinline__ i32 lpc_residual_at(const ChanState &cs, int o, int i) {
+    const i32 x = sample_at(cs, i);
+    if (i < o) return x;
+    i64 pred = 0;
+    for (int t = 0; t < o; t++) pred += (i64)cs.qc[o - 5][t] * (i64)sample_at(cs, i - 1 - t);
+    pred >>= cs.lpc_shift[o - 5];
+    return (i32)((u32)x - (u32)(i32)pred);
+}
+
+// ----------------------------------------------------------------------------
+// Chunk loop of one analysis pass.  With two channels in the group the even warps take channel
+// 0 and the odd warps channel 1, so a thread accumulates for one channel only and flushes once
+// (per 64 rounds: the 32-bit partial sums hold at least 64 chunks).  The unrolled body sees full
+// chunks only; the < 16 samples behind the last full chunk are added by the channel's last warp,
+// one lane per sample, through the scalar functions above.
+// ----------------------------------------------------------------------------
+template <class Reset, class Body, class Tail, class Flush>
+__device__ __forceinline__ void for_chunks(const Smem &s, int nch, Reset &&reset, Body &&body, Tail &&tailfn, Flush &&flush) {
+    const int wid = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int c = nch == 2 ? (wid & 1) : 0;
+    const int wi = nch == 2 ? (wid >> 1) : wid;
+    const int nthr = nch == 2 ? NT / 2 : NT;
+    const int ti = wi * 32 + lane;
+    const bool tail_warp = wi == nthr / 32 - 1;
+    const int nfull = s.cs[c].nfull;
+    int base = 0;
+    do {
+        reset();
+        const int end = min(nfull, base + nthr * 64);
+        for (int chunk = base + ti; chunk < end; chunk += nthr) body(c, chunk);
+        if (end == nfull && tail_warp && lane < s.cs[c].tail) tailfn(c, nfull * CH + lane);
+        flush(c);
+        base = end;
+    } while (base < nfull);
 }
 
 // ---- pass 1: fixed-predictor statistics (sum|r|, OR|r|) + autocorrelation (lpc.rs:213-221) ----
 template <int P>
-__device__ void pass1(Smem &s, int nch, int total_items) {
+__device__ void pass1(Smem &s, int nch) {
     constexpr int NH = P > 4 ? P : 4;
     u32 fsum[5], forr[5];               // |r| <= 2^20 for the fixed predictors: 2^24 per chunk
     double acc[P + 1];
     const int lane = threadIdx.x & 31;
-    for_items(
-        s, nch, total_items,
+    for_chunks(
+        s, nch,
         [&]() {
 #pragma unroll
             for (int o = 0; o < 5; o++) { fsum[o] = 0; forr[o] = 0; }
@@ -314,27 +354,38 @@ __device__ void pass1(Smem &s, int nch, int total_items) {
         [&](int c, int chunk) {
             const ChanState &cs = s.cs[c];
             const int i0 = chunk * CH;
-            const int nv = min(CH, cs.n - i0);
             i32 x[NH + CH];
             load_x<NH>(cs, i0, x);
             if constexpr (P > 0) {
                 // exact: |x| <= 2^16, so every partial sum is an integer far below 2^53
-                double xd[NH + CH];
+                double w[P + CH];
 #pragma unroll
-                for (int i = 0; i < NH + CH; i++) xd[i] = (double)x[i];
+                for (int t = 0; t < P; t++) w[t] = cvt_f64(x[NH - P + t]);
 #pragma unroll
                 for (int j = 0; j < CH; j++) {
+                    w[P + j] = cvt_f64(x[NH + j]);
 #pragma unroll
-                    for (int l = 0; l <= P; l++) acc[l] = __fma_rn(xd[NH + j], xd[NH + j - l], acc[l]);
+                    for (int l = 0; l <= P; l++) acc[l] = __fma_rn(w[P + j], w[P + j - l], acc[l]);
                 }
             }
             fixed_chunk(x + (NH - 4), i0 == 0, [&](int j, i32 r0, i32 r1, i32 r2, i32 r3, i32 r4) {
-                if (j < nv) {
-                    const u32 a0 = (u32)abs(r0), a1 = (u32)abs(r1), a2 = (u32)abs(r2), a3 = (u32)abs(r3), a4 = (u32)abs(r4);
-                    fsum[0] += a0; fsum[1] += a1; fsum[2] += a2; fsum[3] += a3; fsum[4] += a4;
-                    forr[0] |= a0; forr[1] |= a1; forr[2] |= a2; forr[3] |= a3; forr[4] |= a4;
-                }
+                const u32 a0 = (u32)abs(r0), a1 = (u32)abs(r1), a2 = (u32)abs(r2), a3 = (u32)abs(r3), a4 = (u32)abs(r4);
+                fsum[0] += a0; fsum[1] += a1; fsum[2] += a2; fsum[3] += a3; fsum[4] += a4;
+                forr[0] |= a0; forr[1] |= a1; forr[2] |= a2; forr[3] |= a3; forr[4] |= a4;
             });
+        },
+        [&](int c, int i) {
+            const ChanState &cs = s.cs[c];
+#pragma unroll
+            for (int o = 0; o < 5; o++) {
+                const u32 a = (u32)abs(fixed_residual_at(cs, o, i));
+                fsum[o] += a; forr[o] |= a;
+            }
+            if constexpr (P > 0) {
+                const double xi = (double)sample_at(cs, i);
+#pragma unroll
+                for (int l = 0; l <= P; l++) acc[l] = __fma_rn(xi, (double)sample_at(cs, i - l), acc[l]);
+            }
         },
         [&](int c) {
             ChanState &cs = s.cs[c];
@@ -356,13 +407,13 @@ __device__ void pass1(Smem &s, int nch, int total_items) {
 
 // ---- pass 2: LPC candidates 5..P: sum|r|, OR|r| and sum(w >> j) for the guessed window ----
 template <int P>
-__device__ void pass2(Smem &s, int nch, int total_items) {
+__device__ void pass2(Smem &s, int nch) {
     constexpr int NO = P - 4;
     // 32-bit partial sums: only candidates with OR|r| < 2^21 are ever used (after_pass2), 2^25 per chunk
     u32 lsum[NO], lt0[NO], lt1[NO], lorr[NO];
     const int lane = threadIdx.x & 31;
-    for_items(
-        s, nch, total_items,
+    for_chunks(
+        s, nch,
         [&]() {
 #pragma unroll
             for (int i = 0; i < NO; i++) { lsum[i] = 0; lt0[i] = 0; lt1[i] = 0; lorr[i] = 0; }
@@ -370,27 +421,32 @@ __device__ void pass2(Smem &s, int nch, int total_items) {
         [&](int c, int chunk) {
             const ChanState &cs = s.cs[c];
             const int i0 = chunk * CH;
-            const int nv = min(CH, cs.n - i0);
             i32 x[P + CH];
             load_x<P>(cs, i0, x);
-            double xd[P + CH];
-#pragma unroll
-            for (int i = 0; i < P + CH; i++) xd[i] = (double)x[i];
             ForOrders<5, P>::run([&](auto oc) {
                 constexpr int O = decltype(oc)::value;
                 if (cs.lpc_ok[O - 5]) {
                     const int j0 = cs.lpc_j0[O - 5];
                     u32 sa = lsum[O - 5], t0 = lt0[O - 5], t1 = lt1[O - 5], orr = lorr[O - 5];
-                    lpc_chunk<O, P>(x, xd, i0 == 0, cs.qd[O - 5], [&](int j, i32 r) {
-                        if (j < nv) {
-                            const u32 a = (u32)abs(r);
-                            const u32 w = a + (u32)(r >> 31);          // |r| - [r < 0]
-                            sa += a; orr |= a;
-                            const u32 ws = w >> j0;
-                            t0 += ws; t1 += ws >> 1;
-                        }
+                    lpc_chunk<O, P>(x, i0 == 0, cs.qd[O - 5], [&](int j, i32 r) {
+                        const u32 a = (u32)abs(r);
+                        const u32 ws = (a + (u32)(r >> 31)) >> j0;     // w = |r| - [r < 0]
+                        sa += a; orr |= a;
+                        t0 += ws; t1 += ws >> 1;
                     });
                     lsum[O - 5] = sa; lt0[O - 5] = t0; lt1[O - 5] = t1; lorr[O - 5] = orr;
+                }
+            });
+        },
+        [&](int c, int i) {
+            const ChanState &cs = s.cs[c];
+            ForOrders<5, P>::run([&](auto oc) {
+                constexpr int O = decltype(oc)::value;
+                if (cs.lpc_ok[O - 5]) {
+                    const i32 r = lpc_residual_at(cs, O, i);
+                    const u32 a = (u32)abs(r);
+                    const u32 ws = (a + (u32)(r >> 31)) >> cs.lpc_j0[O - 5];
+                    lsum[O - 5] += a; lorr[O - 5] |= a; lt0[O - 5] += ws; lt1[O - 5] += ws >> 1;
                 }
             });
         },
@@ -426,36 +482,30 @@ __device__ __forceinline__ void cand_chunk(const ChanState &cs, int i0, const do
         constexpr int H = MODE <= 8 ? 8 : 12;
         i32 x[H + CH];
         load_x<H>(cs, i0, x);
-        double xd[H + CH];
-#pragma unroll
-        for (int i = 0; i < H + CH; i++) xd[i] = (double)x[i];
-        lpc_chunk<MODE, H>(x, xd, i0 == 0, qd, fn);
+        lpc_chunk<MODE, H>(x, i0 == 0, qd, fn);
     }
 }
 
 // ---- pass 3: exact max|r| and S = sum(w >> j) for one still-open candidate per channel ----
 template <int P>
-__device__ void pass3(Smem &s, int nch, int total_items) {
+__device__ void pass3(Smem &s, int nch) {
     u64 S;
     u32 mx;
     const int lane = threadIdx.x & 31;
-    for_items(
-        s, nch, total_items, [&]() { S = 0; mx = 0; },
+    for_chunks(
+        s, nch, [&]() { S = 0; mx = 0; },
         [&](int c, int chunk) {
             const ChanState &cs = s.cs[c];
             const int cand = cs.ex_cand;
             if (cand < 0) return;
             const int i0 = chunk * CH;
-            const int nv = min(CH, cs.n - i0);
             const int k = cs.cand_k[cand];
             const int jj = k >= 1 ? k - 1 : 0;
-            u32 acc = 0;
+            u64 acc = 0;
             auto fn = [&](int j, i32 r) {
-                if (j < nv) {
-                    const u32 a = (u32)abs(r);
-                    mx = max(mx, a);
-                    acc += (a + (u32)(r >> 31)) >> jj;
-                }
+                const u32 a = (u32)abs(r);
+                mx = max(mx, a);
+                acc += (a + (u32)(r >> 31)) >> jj;
             };
             const int mode = cand - 1;                 // fixed 0..4 -> 0..4, lpc 5..12 -> 5..12
             const double *qd = mode >= 5 ? cs.qd[mode - 5] : nullptr;
@@ -475,6 +525,18 @@ __device__ void pass3(Smem &s, int nch, int total_items) {
                     break;
             }
             S += acc;
+        },
+        [&](int c, int i) {
+            const ChanState &cs = s.cs[c];
+            const int cand = cs.ex_cand;
+            if (cand < 0) return;
+            const int k = cs.cand_k[cand];
+            const int jj = k >= 1 ? k - 1 : 0;
+            const int mode = cand - 1;
+            const i32 r = mode <= 4 ? fixed_residual_at(cs, mode, i) : lpc_residual_at(cs, mode, i);
+            const u32 a = (u32)abs(r);
+            mx = max(mx, a);
+            S += (a + (u32)(r >> 31)) >> jj;
         },
         [&](int c) {
             ChanState &cs = s.cs[c];
@@ -507,7 +569,7 @@ __device__ void after_pass1(ChanState &cs, int P, int fmax, bool lpc_on) {
 }
 
 // after pass 2: resolve the LPC candidates (encoder.rs:262-286)
-__device__ void after_pass2(ChanState &cs, int P) {
+__device__ void after_pass2(ChanState &cs, int P, u32 *counters) {
     const u32 n = (u32)cs.n;
     for (int o = 5; o <= P; o++) {
         const int i = o - 5, c = 1 + o;
@@ -523,8 +585,10 @@ __device__ void after_pass2(ChanState &cs, int P) {
             const u64 S = jj == cs.lpc_j0[i] ? cs.l_t0[i] : cs.l_t1[i];
             cs.cand_state[c] = CS_EXACT;
             cs.cand_size[c] = rice_bytes(S, cs.l_sum[i], n, k);
+            atomicAdd(counters + 2, 1u);
         } else {
-            cs.cand_state[c] = CS_BOUNDED;                            // window miss or 2^19 <= max|r| < 2^20
+            cs.cand_state[c] = CS_BOUNDED;
+            atomicAdd(counters + 3, 1u);                            // window miss or 2^19 <= max|r| < 2^20
         }
     }
 }
@@ -532,7 +596,7 @@ __device__ void after_pass2(ChanState &cs, int P) {
 // Pick the next candidate that still needs an exact evaluation: bounded, and its lower bound
 // does not exceed the best upper bound (otherwise it can never be the strictly-smallest one).
 // Among those the one with the smallest lower bound goes first (it tightens the bound most).
-__device__ int next_open_candidate(ChanState &cs, bool prune) {
+__device__ int next_open_candidate(ChanState &cs, bool prune, u32 *counters) {
     const u32 n = (u32)cs.n;
     i64 best_ub = INT64_MAX;
     for (int j = 0; j < NCAND; j++) {
@@ -551,9 +615,10 @@ __device__ int next_open_candidate(ChanState &cs, bool prune) {
         if (cs.cand_state[j] != CS_BOUNDED) continue;
         i64 lb, ub;
         rice_bounds(cs.cand_sumabs[j], n, cs.cand_k[j], lb, ub);
-        if (prune && lb > best_ub) { cs.cand_state[j] = CS_ABSENT; continue; }   // provably not the winner
+        if (prune && lb > best_ub) { cs.cand_state[j] = CS_ABSENT; atomicAdd(counters + 5, 1u); continue; }   // provably not the winner
         if (lb < pick_lb) { pick_lb = lb; pick = j; }
     }
+    if (pick >= 1 && pick <= 5) atomicAdd(counters + 4, 1u);
     return pick;
 }
 
@@ -583,7 +648,7 @@ __device__ __forceinline__ void chunk_codes(const ChanState &cs, int i0, const d
     });
 }
 
-template <bool WINDOWED>
+template <bool WINDOWED, bool MASKED>
 __device__ __forceinline__ void emit_chunk(u32 *ring, const u32 (&u)[CH], int nv, int k, bool raw, u64 start,
                                            u32 wlo, u32 whi) {
     u32 w = (u32)(start >> 5);
@@ -605,7 +670,7 @@ __device__ __forceinline__ void emit_chunk(u32 *ring, const u32 (&u)[CH], int nv
     };
 #pragma unroll
     for (int j = 0; j < CH; j++) {
-        if (j < nv) {
+        if (!MASKED || j < nv) {
             if (raw) {
                 put(u[j], 16);
             } else {                               // encode_sample, rice.rs:94-114
@@ -662,7 +727,8 @@ __device__ void pack_channel(Smem &s, const ChanState &cs, const ChanResult &cr,
     const double *qd = s.wqd;
     for (int sc = 0; sc < nsc; sc++) {
         const int i0 = sc * per_sc + tid * CH;
-        const int nv = max(0, min(CH, n - i0));
+        const bool last = sc == nsc - 1;               // only the last super-chunk has short or absent chunks
+        const int nv = last ? max(0, min(CH, n - i0)) : CH;
         u32 u[CH];
         u32 tb = 0;
         if (nv > 0) {
@@ -684,6 +750,11 @@ __device__ void pack_channel(Smem &s, const ChanState &cs, const ChanResult &cr,
             }
             if (raw) {
                 tb = 16u * (u32)nv;
+            } else if (!last) {
+                u32 qs = 0;
+#pragma unroll
+                for (int j = 0; j < CH; j++) qs += u[j] >> k;
+                tb = qs + (u32)CH * (1u + (u32)k);
             } else {
 #pragma unroll
                 for (int j = 0; j < CH; j++)
@@ -717,7 +788,8 @@ __device__ void pack_channel(Smem &s, const ChanState &cs, const ChanResult &cr,
         u32 wlo = wfl;
         if (wlast - wlo <= (u32)RING_WORDS) {
             // common case: the whole super-chunk fits the staging ring
-            if (nv > 0) emit_chunk<false>(s.ring, u, nv, k, raw, start, 0, 0);
+            if (!last) emit_chunk<false, false>(s.ring, u, CH, k, raw, start, 0, 0);
+            else if (nv > 0) emit_chunk<false, true>(s.ring, u, nv, k, raw, start, 0, 0);
             __syncthreads();
             const u32 wend = (u32)(end_sc >> 5);
             flush_ring(s.ring, obase, abase, lo, hi, wlo, wend);
@@ -726,7 +798,7 @@ __device__ void pack_channel(Smem &s, const ChanState &cs, const ChanResult &cr,
         } else {
             for (;;) {
                 const u32 whi = wlo + RING_WORDS;
-                if (nv > 0) emit_chunk<true>(s.ring, u, nv, k, raw, start, wlo, whi);
+                if (nv > 0) emit_chunk<true, true>(s.ring, u, nv, k, raw, start, wlo, whi);
                 __syncthreads();
                 const u32 wend = min(whi, (u32)(end_sc >> 5));
                 flush_ring(s.ring, obase, abase, lo, hi, wlo, wend);
@@ -991,6 +1063,7 @@ __global__ void __launch_bounds__(NT, 1) k_encode_frames(const EncodeParams p) {
             continue;
         }
 
+        if (tid == 0) atomicAdd(p.counters, 1u);
         // mid/side decision, encoder.rs:94-100, 131-153
         int ms = 0;
         if (C == 2) {
@@ -1011,7 +1084,8 @@ __global__ void __launch_bounds__(NT, 1) k_encode_frames(const EncodeParams p) {
                 u32 cl = len > c ? (len - c + C - 1) / C : 0;
                 if (ms) cl = len >> 1;                                      // zip in to_mid_side truncates, encoder.rs:160-167
                 cs.n = (int)cl;
-                cs.nchunks = (int)((cl + CH - 1) / CH);
+                cs.nfull = (int)(cl / CH);
+                cs.tail = (int)(cl % CH);
                 cs.msmode = ms ? (c == 0 ? 1 : 2) : 0;
                 cs.pa = ms ? planes : planes + (size_t)c * stride;
                 cs.pb = planes + stride;
@@ -1021,17 +1095,10 @@ __global__ void __launch_bounds__(NT, 1) k_encode_frames(const EncodeParams p) {
                 cs.ex_cand = -1; cs.ex_s = 0; cs.ex_max = 0;
             }
             __syncthreads();
-            if (tid == 0) {
-                int base = 0;
-                for (int q = 0; q < nch; q++) { s.cs[q].item_base = base; base += (s.cs[q].nchunks + 31) & ~31; }
-                s.scan_total = (u32)base;
-            }
-            __syncthreads();
-            const int total_items = (int)s.scan_total;
             bool any_lpc = false;
             for (int q = 0; q < nch; q++) any_lpc |= lpc_on && s.cs[q].n > 5;
-            if (any_lpc) pass1<P>(s, nch, total_items);
-            else pass1<0>(s, nch, total_items);
+            if (any_lpc) pass1<P>(s, nch);
+            else pass1<0>(s, nch);
             __syncthreads();
             if (tid < nch && s.cs[tid].n > 0) after_pass1(s.cs[tid], P, fmax, lpc_on);
             __syncthreads();
@@ -1039,9 +1106,9 @@ __global__ void __launch_bounds__(NT, 1) k_encode_frames(const EncodeParams p) {
             for (int q = 0; q < nch; q++)
                 for (int o = 0; o < NLPC; o++) run2 |= s.cs[q].n > 0 && s.cs[q].lpc_ok[o] != 0;
             if (run2) {
-                if constexpr (P > 0) pass2<P>(s, nch, total_items);
+                if constexpr (P > 0) pass2<P>(s, nch);
                 __syncthreads();
-                if (tid < nch && s.cs[tid].n > 0) after_pass2(s.cs[tid], P);
+                if (tid < nch && s.cs[tid].n > 0) after_pass2(s.cs[tid], P, p.counters);
             }
             // exact evaluation of whatever is still open (bounded candidates that can still win)
             for (;;) {
@@ -1050,13 +1117,14 @@ __global__ void __launch_bounds__(NT, 1) k_encode_frames(const EncodeParams p) {
                 __syncthreads();
                 if (tid < nch && s.cs[tid].n > 0) {
                     ChanState &cs = s.cs[tid];
-                    cs.ex_cand = next_open_candidate(cs, prune);
+                    cs.ex_cand = next_open_candidate(cs, prune, p.counters);
                     cs.ex_s = 0; cs.ex_max = 0;
                     if (cs.ex_cand >= 0) atomicOr(reinterpret_cast<u32 *>(&s.more), 1u);
                 }
                 __syncthreads();
                 if (!s.more) break;
-                pass3<P>(s, nch, total_items);
+                if (tid == 0) atomicAdd(p.counters + 1, 1u);
+                pass3<P>(s, nch);
                 __syncthreads();
                 if (tid < nch && s.cs[tid].n > 0) after_pass3(s.cs[tid]);
             }

@@ -99,7 +99,8 @@ struct flo_ctx {
     std::mutex mu;
     cudaStream_t own_stream = nullptr, stream = nullptr;
     cudaEvent_t ev[8] = {};
-    DevBuf in, out, meta, tracks, frames, ctrl, fexcl, fsize, segcrc, foff, plane, cres, report;
+    DevBuf in, out, meta, tracks, frames, ctrl, fexcl, fsize, foff, plane, cres, report;
+    uint64_t counters[8] = {0, 0, 0, 0, 0, 0, 0, 0};
     HostBuf h_small, h_out;
     bool report_on = false;
     uint32_t report_frames = 0;
@@ -144,7 +145,7 @@ extern "C" void flo_ctx_destroy(flo_ctx *c) {
     if (!c) return;
     cudaSetDevice(c->device);
     cudaDeviceSynchronize();
-    for (DevBuf *b : {&c->in, &c->out, &c->meta, &c->tracks, &c->frames, &c->ctrl, &c->fexcl, &c->fsize, &c->segcrc,
+    for (DevBuf *b : {&c->in, &c->out, &c->meta, &c->tracks, &c->frames, &c->ctrl, &c->fexcl, &c->fsize,
                       &c->foff, &c->plane, &c->cres, &c->report})
         b->release();
     c->h_small.release();
@@ -166,6 +167,13 @@ extern "C" int flo_ctx_last_timing(flo_ctx *c, float ms[6], uint32_t *launches) 
     std::lock_guard<std::mutex> lk(c->mu);
     if (ms) memcpy(ms, c->ms, sizeof c->ms);
     if (launches) *launches = c->launches;
+    return FLO_OK;
+}
+
+extern "C" int flo_ctx_last_counters(flo_ctx *c, uint64_t out[8]) {
+    if (!c || !out) { set_err("bad argument"); return FLO_ERR_ARG; }
+    std::lock_guard<std::mutex> lk(c->mu);
+    memcpy(out, c->counters, sizeof c->counters);
     return FLO_OK;
 }
 
@@ -287,10 +295,10 @@ static int encode_batch_impl(flo_ctx *c, const flo_track *tracks, size_t n_track
     const uint32_t NF = (uint32_t)L.n_frames, NSEG = (uint32_t)L.n_segs, NTR = (uint32_t)n_tracks;
     if ((rc = c->tracks.reserve(sizeof(TrackDev) * n_tracks))) return rc;
     if ((rc = c->frames.reserve(sizeof(uint2) * std::max<uint64_t>(NF, 1)))) return rc;
-    if ((rc = c->ctrl.reserve(8ull * NF + 64))) return rc;             // status words + ticket + err
+    const size_t ctrl_bytes = 8ull * NF + 64 + 4ull * n_tracks;        // status words, ticket, err, counters, track CRCs
+    if ((rc = c->ctrl.reserve(ctrl_bytes))) return rc;
     if ((rc = c->fexcl.reserve(8ull * std::max<uint64_t>(NF, 1)))) return rc;
     if ((rc = c->fsize.reserve(4ull * std::max<uint64_t>(NF, 1)))) return rc;
-    if ((rc = c->segcrc.reserve(4ull * std::max<uint64_t>(NSEG, 1)))) return rc;
     if ((rc = c->foff.reserve(16ull * n_tracks))) return rc;
     if ((rc = c->meta.reserve(std::max<uint64_t>(L.meta_total, 1)))) return rc;
     if ((rc = c->h_small.reserve(sizeof(TrackDev) * n_tracks + L.meta_total + 16ull * n_tracks + 64))) return rc;
@@ -334,7 +342,7 @@ static int encode_batch_impl(flo_ctx *c, const flo_track *tracks, size_t n_track
         if (tracks[t].meta_len) memcpy(hmeta + L.tr[t].meta_off, tracks[t].meta, tracks[t].meta_len);
     CK(cudaMemcpyAsync(c->tracks.p, hs, sizeof(TrackDev) * n_tracks, cudaMemcpyHostToDevice, st));
     if (L.meta_total) CK(cudaMemcpyAsync(c->meta.p, hmeta, L.meta_total, cudaMemcpyHostToDevice, st));
-    CK(cudaMemsetAsync(c->ctrl.p, 0, 8ull * NF + 64, st));
+    CK(cudaMemsetAsync(c->ctrl.p, 0, ctrl_bytes, st));
     CK(cudaEventRecord(c->ev[1], st));
 
     uint32_t launches = 0;
@@ -349,6 +357,7 @@ static int encode_batch_impl(flo_ctx *c, const flo_track *tracks, size_t n_track
     ep.status = (unsigned long long *)c->ctrl.p;
     ep.ticket = (uint32_t *)((uint8_t *)c->ctrl.p + 8ull * NF);
     ep.err = ep.ticket + 1;
+    ep.counters = ep.ticket + 2;
     ep.frame_excl = (unsigned long long *)c->fexcl.p;
     ep.frame_size = (uint32_t *)c->fsize.p;
     ep.plane_scratch = (int16_t *)c->plane.p;
@@ -362,7 +371,7 @@ static int encode_batch_impl(flo_ctx *c, const flo_track *tracks, size_t n_track
     fp.tracks = ep.tracks; fp.n_tracks = NTR; fp.n_frames = NF; fp.level = level; fp.frames = ep.frames;
     fp.out = out; fp.meta = (const uint8_t *)c->meta.p;
     fp.frame_excl = ep.frame_excl; fp.frame_size = ep.frame_size;
-    fp.seg_crc = (uint32_t *)c->segcrc.p; fp.n_segs = NSEG;
+    fp.track_crc = ep.ticket + 16; fp.n_segs = NSEG;
     fp.file_off = (unsigned long long *)c->foff.p;
     fp.file_len = fp.file_off + n_tracks;
 
@@ -384,12 +393,13 @@ static int encode_batch_impl(flo_ctx *c, const flo_track *tracks, size_t n_track
 
     // results: per-track offsets/lengths + error flag
     uint64_t *h_off = (uint64_t *)(hs + align_up(sizeof(TrackDev) * n_tracks + L.meta_total, 16));
-    uint32_t *h_err = (uint32_t *)(h_off + 2 * n_tracks);
+    uint32_t *h_err = (uint32_t *)(h_off + 2 * n_tracks);           // err + 8 counters
     CK(cudaMemcpyAsync(h_off, c->foff.p, 16ull * n_tracks, cudaMemcpyDeviceToHost, st));
-    CK(cudaMemcpyAsync(h_err, ep.err, 4, cudaMemcpyDeviceToHost, st));
+    CK(cudaMemcpyAsync(h_err, ep.err, 4 * 9, cudaMemcpyDeviceToHost, st));
     CK(cudaStreamSynchronize(st));
     if (*h_err) { set_err("device-side consistency check failed (code 0x%08x)", *h_err); return FLO_ERR_INTERNAL; }
     for (size_t t = 0; t < n_tracks; t++) { offsets[t] = h_off[t]; lens[t] = h_off[n_tracks + t]; }
+    for (int i = 0; i < 8; i++) c->counters[i] = h_err[1 + i];
 
     float t_all = 0, t_enc = 0, t_toc = 0, t_crc = 0, t_hdr = 0, t_setup = 0, t_h2d = 0;
     cudaEventElapsedTime(&t_h2d, c->ev[0], c->ev[1]);

@@ -61,6 +61,8 @@ struct EncodeParams {
     ChanResult *cres;                 // per-CTA channel results, 256 entries per CTA
     flo_cand_report *report;          // optional [n_frames][REPORT_CH][NCAND]
     uint32_t *err;                    // device error flag
+    uint32_t *counters;               // [0] loud frames, [1] pass-3 rounds, [2] LPC sizes from the window, [3] window misses,
+                                      // [4] fixed candidates evaluated exactly, [5] candidates pruned by bounds
     uint32_t smem_plane_bytes;        // bytes of dynamic shared memory available for sample planes
 };
 
@@ -74,7 +76,7 @@ struct FinalParams {
     const uint8_t *meta;              // metadata arena
     const unsigned long long *frame_excl;
     const uint32_t *frame_size;
-    uint32_t *seg_crc;                // per CRC segment
+    uint32_t *track_crc;              // per track, zeroed; CRC segments XOR their shifted CRCs in
     uint32_t n_segs;
     unsigned long long *file_off;     // out: per track
     unsigned long long *file_len;     // out: per track

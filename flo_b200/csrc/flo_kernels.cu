@@ -191,7 +191,11 @@ __global__ void __launch_bounds__(CRC_NT) k_crc_segments(const FinalParams p) {
     if (lane == 0) {
         u32 r = ~crc;
         for (u32 i = nblk << 7; i < slen; i++) r = (r >> 8) ^ T[0][(r ^ base[i]) & 0xff];
-        p.seg_crc[seg] = ~r;
+        // crc(A || B) = crc(A) * x^(8 |B|) ^ crc(B)  (mod p): shift this segment's CRC by the bytes behind it
+        // and fold it into the track's CRC; XOR makes the order of the segments irrelevant.
+        const u64 after = dsize - (soff + slen);
+        const u32 shifted = after ? multmodp(x2nmodp(after, 3), ~r) : ~r;
+        atomicXor(&p.track_crc[lo], shifted);
     }
 }
 
@@ -205,13 +209,7 @@ __global__ void k_write_headers(const FinalParams p) {
     const u64 toc_size = 4 + 20ull * tr.n_frames;
     uint8_t *o = p.out + file0;
     if (threadIdx.x == 0) {
-        u32 crc = 0;
-        const u64 nseg = (dsize + CRC_SEG - 1) / CRC_SEG;
-        for (u64 j = 0; j < nseg; j++) {
-            const u64 len = min((u64)CRC_SEG, dsize - j * CRC_SEG);
-            const u32 mul = len == CRC_SEG ? c_powseg : x2nmodp(len, 3);
-            crc = multmodp(mul, crc) ^ p.seg_crc[tr.first_seg + j];
-        }
+        const u32 crc = p.track_crc[t];
         o[0] = 0x46; o[1] = 0x4C; o[2] = 0x4F; o[3] = 0x21;        // "FLO!", types.rs:6
         o[4] = 1; o[5] = 2;                                        // version 1.2, types.rs:12-13
         o[6] = 0; o[7] = 0;                                        // flags: lossless

@@ -62,6 +62,12 @@ class Context:
         d["launches"] = int(n.value)
         return d
 
+    def last_counters(self) -> dict:
+        buf = (C.c_uint64 * 8)()
+        _lib.check(self._L.flo_ctx_last_counters(self._h, buf))
+        keys = ["loud_frames", "exact_rounds", "lpc_window_hits", "lpc_window_misses", "fixed_exact", "pruned"]
+        return {k: int(v) for k, v in zip(keys, buf)}
+
     # -- encode entries ----------------------------------------------------------------
     def encode_batch(self, tracks: Sequence["TrackSpec"], level: int = 5, fmt: int = FMT_F32) -> List[bytes]:
         n = len(tracks)

@@ -109,6 +109,11 @@ int flo_ctx_set_stream(flo_ctx *ctx, void *cuda_stream);
  * launched by that call. */
 int flo_ctx_last_timing(flo_ctx *ctx, float ms[6], uint32_t *launches);
 
+/* Analysis counters of the last batch call (diagnostics): [0] non-silent frames, [1] exact-size
+ * re-evaluation rounds, [2] LPC candidates sized in the single pass, [3] LPC candidates that needed the
+ * exact pass, [4] fixed candidates evaluated exactly, [5] candidates excluded by size bounds. */
+int flo_ctx_last_counters(flo_ctx *ctx, uint64_t out[8]);
+
 /* Per-frame analysis report of the last batch call, for parity tests: for
  * global frame g and channel c (< 8), candidate j (raw, fixed 0..4, lpc
  * 5..12 -> j = 0..13): k and encoded size (-1 = candidate absent).  Must be
