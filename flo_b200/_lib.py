@@ -6,7 +6,8 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-SO_PATH = os.path.join(_HERE, "libflo_b200.so")
+# FLO_B200_SO selects an experimental build of the same library (see build.py); never a different implementation
+SO_PATH = os.environ.get("FLO_B200_SO") or os.path.join(_HERE, "libflo_b200.so")
 
 FMT_F32, FMT_PCM16 = 0, 1
 

@@ -36,22 +36,27 @@ def stale() -> bool:
     return any(os.path.getmtime(d) > t for d in deps)
 
 
-def build(force: bool = False, verbose: bool = False) -> str:
-    if not force and not stale():
+def build(force: bool = False, verbose: bool = False, defines: tuple = (), out: str = SO) -> str:
+    """defines/out are for experiments (e.g. defines=("FLO_NT=1024",), out=".../libflo_b200_x.so")."""
+    if not force and not stale() and out == SO:
         return SO
     objs = []
+    tag = "" if out == SO else "_" + os.path.basename(out).replace(".so", "")
     for src in SOURCES:
-        obj = os.path.join(CSRC, src.replace(".cu", ".o"))
-        cmd = [nvcc(), *NVCC_FLAGS, "-c", os.path.join(CSRC, src), "-o", obj]
+        obj = os.path.join(CSRC, src.replace(".cu", tag + ".o"))
+        cmd = [nvcc(), *NVCC_FLAGS, *[f"-D{d}" for d in defines], "-c", os.path.join(CSRC, src), "-o", obj]
         if verbose:
             cmd.insert(1, "-Xptxas=-v")
             print(" ".join(cmd))
         subprocess.check_call(cmd)
         objs.append(obj)
-    cmd = [nvcc(), "-shared", "-o", SO, *objs, "-cudart", "static"]
+    cmd = [nvcc(), "-shared", "-o", out, *objs, "-cudart", "static"]
     subprocess.check_call(cmd)
-    return SO
+    return out
 
 
 if __name__ == "__main__":
-    print(build(force="--force" in sys.argv, verbose="-v" in sys.argv))
+    defs = tuple(a[2:] for a in sys.argv[1:] if a.startswith("-D"))
+    outs = [a[6:] for a in sys.argv[1:] if a.startswith("--out=")]
+    print(build(force="--force" in sys.argv, verbose="-v" in sys.argv, defines=defs,
+                out=os.path.join(HERE, outs[0]) if outs else SO))

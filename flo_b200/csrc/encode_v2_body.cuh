@@ -43,12 +43,10 @@ struct Smem {
     ChanState cs[GROUP];
     i32 wcoef[MAXORD];                // winner's coefficients while packing
     double wqd[MAXORD];
-    u32 scan_warp[NWARP];
-    u32 scan_total;
+    u32 scan_warp[2][NWARP];
     u32 g;                            // current global frame
     i32 ms;                           // mid/side chosen (encoder.rs:94-100)
     i32 loud;
-    i32 more;                         // pass-3 rounds pending
     u64 ms_var[3];
     u64 frame_excl;                   // exclusive prefix of frame sizes
     u32 ring[RING_WORDS];             // bit-packer staging ring (big-endian bit order words)
@@ -126,36 +124,48 @@ __device__ __forceinline__ void rice_bounds(u64 sum_abs, u32 n, int k, i64 &lb, 
 // separately.  The recursion is prefix consistent (the order-m result is the state after
 // iteration m-1), so one run to order P yields every order 5..P.  Also derives, per order,
 // the guessed shift window for the single-pass size evaluation from the prediction error.
-__device__ void levinson_all_orders(ChanState &cs, int P) {
+template <int P>
+__device__ void levinson_all_orders(ChanState &cs) {
     for (int o = 0; o < NLPC; o++) { cs.lpc_ok[o] = 0; cs.lpc_shift[o] = 0; cs.lpc_j0[o] = 0; }
     if (cs.ac[0] == 0) return;
-    double a[MAXORD], nc[MAXORD];
-    for (int i = 0; i < MAXORD; i++) a[i] = 0.0;
-    double err = (double)cs.ac[0];
+    double a[P > 0 ? P : 1], nc[P > 0 ? P : 1], acd[P + 1];
+#pragma unroll
+    for (int i = 0; i < P; i++) a[i] = 0.0;
+#pragma unroll
+    for (int i = 0; i <= P; i++) acd[i] = (double)cs.ac[i];
+    double err = acd[0];
+    bool alive = true;
+#pragma unroll
     for (int i = 0; i < P; i++) {
-        double lambda = (double)cs.ac[i + 1];
-        for (int j = 0; j < i; j++) lambda = __dsub_rn(lambda, __dmul_rn(a[j], (double)cs.ac[i - j]));
-        if (fabs(err) < 1e-10) return;
-        double gamma = __ddiv_rn(lambda, err);
-        if (fabs(gamma) >= 1.0) return;
+        if (!alive) break;
+        double lambda = acd[i + 1];
+#pragma unroll
+        for (int j = 0; j < i; j++) lambda = __dsub_rn(lambda, __dmul_rn(a[j], acd[i - j]));
+        if (fabs(err) < 1e-10) { alive = false; break; }
+        const double gamma = __ddiv_rn(lambda, err);
+        if (fabs(gamma) >= 1.0) { alive = false; break; }
         nc[i] = gamma;
+#pragma unroll
         for (int j = 0; j < i; j++) nc[j] = __dsub_rn(a[j], __dmul_rn(gamma, a[i - 1 - j]));
+#pragma unroll
         for (int j = 0; j <= i; j++) a[j] = nc[j];
         err = __dmul_rn(err, __dsub_rn(1.0, __dmul_rn(gamma, gamma)));
         const int o = i + 1;
         if (o >= 5) {
             double mx = 0.0;
-            for (int j = 0; j < o; j++) { double t = fabs(a[j]); if (t == t && t > mx) mx = t; }
+#pragma unroll
+            for (int j = 0; j <= i; j++) { double t = fabs(a[j]); if (t == t && t > mx) mx = t; }
             if (mx == 0.0 || isinf(mx)) continue;
             // shift = min(floor(log2(2^30 / max)) as u8, 15); floor(log2(v)) of a positive finite
             // double is its binary exponent (|a_j| <= C(12,6) = 924 makes this 15 in practice).
-            double v = __ddiv_rn(1073741824.0, mx);
-            int e = isinf(v) ? 255 : ilogb(v);
-            int shift = e < 0 ? 0 : (e > 15 ? 15 : e);
-            double scale = (double)(1ll << shift);
-            for (int j = 0; j < o; j++) {
-                double q = round(__dmul_rn(a[j], scale));       // f64::round: half away from zero
-                i32 qi = q >= 2147483647.0 ? 2147483647 : (q <= -2147483648.0 ? (-2147483647 - 1) : (i32)q);
+            const double v = __ddiv_rn(1073741824.0, mx);
+            const int e = isinf(v) ? 255 : ilogb(v);
+            const int shift = e < 0 ? 0 : (e > 15 ? 15 : e);
+            const double scale = (double)(1ll << shift);
+#pragma unroll
+            for (int j = 0; j <= i; j++) {
+                const double q = round(__dmul_rn(a[j], scale));       // f64::round: half away from zero
+                const i32 qi = q >= 2147483647.0 ? 2147483647 : (q <= -2147483648.0 ? (-2147483647 - 1) : (i32)q);
                 cs.qc[o - 5][j] = qi;
                 cs.qd[o - 5][j] = ldexp((double)qi, -shift);
             }
@@ -163,9 +173,15 @@ __device__ void levinson_all_orders(ChanState &cs, int P) {
             cs.lpc_ok[o - 5] = 1;
             // Heuristic only (exactness never depends on it): mean|r| ~ 0.64 * rms(r), rms^2 ~ err / n.
             // The window {j0, j0+1} must contain max(k-1, 0); a miss is re-evaluated exactly in pass 3.
-            double rms2 = err > 0.0 ? err / (double)cs.n : 0.0;
-            double lg = rms2 > 1e-30 ? 0.5 * log2(rms2) - 0.64 : -10.0;
-            int j0 = (int)floor(lg - 0.5);
+            // log2 via the exponent and a linear mantissa term is accurate to 0.09, ample here.
+            const double rms2 = err > 0.0 ? err / (double)cs.n : 0.0;
+            double lg = -10.0;
+            if (rms2 > 1e-30) {
+                int ex;
+                const double m = frexp(rms2, &ex);                    // rms2 = m 2^ex, m in [0.5, 1)
+                lg = 0.5 * ((double)ex + 2.0 * m - 2.0) - 0.64;
+            }
+            const int j0 = (int)floor(lg - 0.5);
             cs.lpc_j0[o - 5] = j0 < 0 ? 0 : (j0 > 14 ? 14 : j0);
         }
     }
@@ -550,7 +566,8 @@ __device__ void pass3(Smem &s, int nch) {
 // candidate bookkeeping (one thread per channel)
 // ----------------------------------------------------------------------------
 // after pass 1: k of every fixed candidate, raw size; then Levinson
-__device__ void after_pass1(ChanState &cs, int P, int fmax, bool lpc_on) {
+template <int P>
+__device__ void after_pass1(ChanState &cs, int fmax, bool lpc_on) {
     const u32 n = (u32)cs.n;
     for (int j = 0; j < NCAND; j++) { cs.cand_state[j] = CS_ABSENT; cs.cand_k[j] = 0; cs.cand_size[j] = -1; cs.cand_sumabs[j] = 0; }
     cs.cand_state[0] = CS_EXACT;
@@ -562,7 +579,7 @@ __device__ void after_pass1(ChanState &cs, int P, int fmax, bool lpc_on) {
     }
     for (int o = 0; o < NLPC; o++) cs.lpc_ok[o] = 0;
     if (lpc_on && cs.n > 5) {
-        levinson_all_orders(cs, P);
+        if constexpr (P > 0) levinson_all_orders<P>(cs);
         for (int o = 5; o <= P; o++)
             if (cs.n <= o) cs.lpc_ok[o - 5] = 0;                      // encoder.rs:255-257
     }
@@ -761,29 +778,29 @@ __device__ void pack_channel(Smem &s, const ChanState &cs, const ChanResult &cr,
                     if (j < nv) tb += (u[j] >> k) + 1u + (u32)k;
             }
         }
-        // block exclusive scan of the chunk bit counts
+        // block exclusive scan of the chunk bit counts: warp scan, one barrier, then every warp scans the
+        // 16 warp totals itself.  The totals are double buffered by round parity, and the ring words flushed
+        // in the previous round are only touched again behind this round's barrier.
         u32 inc = tb;
 #pragma unroll
         for (int o = 1; o < 32; o <<= 1) {
             u32 t = __shfl_up_sync(0xffffffffu, inc, o);
             if (lane >= o) inc += t;
         }
-        if (lane == 31) s.scan_warp[wid] = inc;
+        u32 *tot = s.scan_warp[sc & 1];
+        if (lane == 31) tot[wid] = inc;
         __syncthreads();
-        if (wid == 0) {
-            u32 v = lane < NWARP ? s.scan_warp[lane] : 0;
-            u32 vi = v;
+        u32 wv = lane < NWARP ? tot[lane] : 0;
+        u32 wincl = wv;
 #pragma unroll
-            for (int o = 1; o < 32; o <<= 1) {
-                u32 t = __shfl_up_sync(0xffffffffu, vi, o);
-                if (lane >= o) vi += t;
-            }
-            if (lane < NWARP) s.scan_warp[lane] = vi - v;
-            if (lane == NWARP - 1) s.scan_total = vi;
+        for (int o = 1; o < NWARP; o <<= 1) {
+            u32 t = __shfl_up_sync(0xffffffffu, wincl, o);
+            if (lane >= o) wincl += t;
         }
-        __syncthreads();
-        const u64 start = bitpos + s.scan_warp[wid] + (inc - tb);
-        const u64 end_sc = bitpos + s.scan_total;
+        const u32 warp_excl = __shfl_sync(0xffffffffu, wincl - wv, wid);
+        const u32 scan_total = __shfl_sync(0xffffffffu, wincl, NWARP - 1);
+        const u64 start = bitpos + warp_excl + (inc - tb);
+        const u64 end_sc = bitpos + scan_total;
         const u32 wlast = (u32)((end_sc + 31) >> 5);
         u32 wlo = wfl;
         if (wlast - wlo <= (u32)RING_WORDS) {
@@ -793,7 +810,6 @@ __device__ void pack_channel(Smem &s, const ChanState &cs, const ChanResult &cr,
             __syncthreads();
             const u32 wend = (u32)(end_sc >> 5);
             flush_ring(s.ring, obase, abase, lo, hi, wlo, wend);
-            __syncthreads();
             wlo = wend;
         } else {
             for (;;) {
@@ -810,6 +826,7 @@ __device__ void pack_channel(Smem &s, const ChanState &cs, const ChanResult &cr,
         wfl = wlo;
         bitpos = end_sc;
     }
+    __syncthreads();
     if (bitpos & 31) flush_ring(s.ring, obase, abase, lo, hi, wfl, wfl + 1);
     if (tid == 0) {
         const u64 bits = bitpos - (pos & 3ull) * 8ull;
@@ -899,23 +916,7 @@ __device__ void ingest_frame(Smem &s, const T *in, u32 len, u32 C, int16_t *plan
         // vector path: 8 sample-frames per thread step, 16-byte loads, 16-byte plane stores
         if ((reinterpret_cast<uintptr_t>(in) & 15) == 0) {
             const u32 ngrp = nf >> 3;
-            for (u32 gI = tid; gI < ngrp; gI += NT) {
-                float f[16];
-                if constexpr (sizeof(T) == 4) {
-                    const float4 *p = reinterpret_cast<const float4 *>(in) + (size_t)gI * 4;
-                    const float4 a = __ldg(p), b = __ldg(p + 1), c = __ldg(p + 2), d = __ldg(p + 3);
-                    f[0] = a.x; f[1] = a.y; f[2] = a.z; f[3] = a.w; f[4] = b.x; f[5] = b.y; f[6] = b.z; f[7] = b.w;
-                    f[8] = c.x; f[9] = c.y; f[10] = c.z; f[11] = c.w; f[12] = d.x; f[13] = d.y; f[14] = d.z; f[15] = d.w;
-                } else {
-                    const int4 *p = reinterpret_cast<const int4 *>(in) + (size_t)gI * 2;
-                    const int4 a = __ldg(p), b = __ldg(p + 1);
-                    const int wv[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
-#pragma unroll
-                    for (int i = 0; i < 8; i++) {
-                        f[2 * i] = pcm_to_f32((int)(int16_t)(wv[i] & 0xffff));
-                        f[2 * i + 1] = pcm_to_f32(wv[i] >> 16);
-                    }
-                }
+            auto convert = [&](const float (&f)[16], u32 gI) {
                 i32 l[8], r[8];
 #pragma unroll
                 for (int i = 0; i < 8; i++) A.pair(f[2 * i], f[2 * i + 1], l[i], r[i]);
@@ -923,6 +924,37 @@ __device__ void ingest_frame(Smem &s, const T *in, u32 len, u32 C, int16_t *plan
                     make_uint4(pack2(l[0], l[1]), pack2(l[2], l[3]), pack2(l[4], l[5]), pack2(l[6], l[7]));
                 *reinterpret_cast<uint4 *>(planes + stride + (size_t)gI * 8) =
                     make_uint4(pack2(r[0], r[1]), pack2(r[2], r[3]), pack2(r[4], r[5]), pack2(r[6], r[7]));
+            };
+            // two groups per step: both groups' 16-byte loads are issued before either is converted
+            for (u32 gI = tid; gI < ngrp; gI += 2 * NT) {
+                const u32 gJ = gI + NT;
+                const bool two = gJ < ngrp;
+                float f[16], h[16];
+                if constexpr (sizeof(T) == 4) {
+                    const float4 *p = reinterpret_cast<const float4 *>(in) + (size_t)gI * 4;
+                    const float4 *q = reinterpret_cast<const float4 *>(in) + (size_t)(two ? gJ : gI) * 4;
+                    const float4 a = __ldg(p), b = __ldg(p + 1), c = __ldg(p + 2), d = __ldg(p + 3);
+                    const float4 a2 = __ldg(q), b2 = __ldg(q + 1), c2 = __ldg(q + 2), d2 = __ldg(q + 3);
+                    f[0] = a.x; f[1] = a.y; f[2] = a.z; f[3] = a.w; f[4] = b.x; f[5] = b.y; f[6] = b.z; f[7] = b.w;
+                    f[8] = c.x; f[9] = c.y; f[10] = c.z; f[11] = c.w; f[12] = d.x; f[13] = d.y; f[14] = d.z; f[15] = d.w;
+                    h[0] = a2.x; h[1] = a2.y; h[2] = a2.z; h[3] = a2.w; h[4] = b2.x; h[5] = b2.y; h[6] = b2.z; h[7] = b2.w;
+                    h[8] = c2.x; h[9] = c2.y; h[10] = c2.z; h[11] = c2.w; h[12] = d2.x; h[13] = d2.y; h[14] = d2.z; h[15] = d2.w;
+                } else {
+                    const int4 *p = reinterpret_cast<const int4 *>(in) + (size_t)gI * 2;
+                    const int4 *q = reinterpret_cast<const int4 *>(in) + (size_t)(two ? gJ : gI) * 2;
+                    const int4 a = __ldg(p), b = __ldg(p + 1), a2 = __ldg(q), b2 = __ldg(q + 1);
+                    const int wv[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+                    const int wu[8] = {a2.x, a2.y, a2.z, a2.w, b2.x, b2.y, b2.z, b2.w};
+#pragma unroll
+                    for (int i = 0; i < 8; i++) {
+                        f[2 * i] = pcm_to_f32((int)(int16_t)(wv[i] & 0xffff));
+                        f[2 * i + 1] = pcm_to_f32(wv[i] >> 16);
+                        h[2 * i] = pcm_to_f32((int)(int16_t)(wu[i] & 0xffff));
+                        h[2 * i + 1] = pcm_to_f32(wu[i] >> 16);
+                    }
+                }
+                convert(f, gI);
+                if (two) convert(h, gJ);
             }
             done = ngrp << 3;
         }
@@ -1100,7 +1132,7 @@ __global__ void __launch_bounds__(NT, 1) k_encode_frames(const EncodeParams p) {
             if (any_lpc) pass1<P>(s, nch);
             else pass1<0>(s, nch);
             __syncthreads();
-            if (tid < nch && s.cs[tid].n > 0) after_pass1(s.cs[tid], P, fmax, lpc_on);
+            if (tid < nch && s.cs[tid].n > 0) after_pass1<P>(s.cs[tid], fmax, lpc_on);
             __syncthreads();
             bool run2 = false;
             for (int q = 0; q < nch; q++)
@@ -1108,25 +1140,29 @@ __global__ void __launch_bounds__(NT, 1) k_encode_frames(const EncodeParams p) {
             if (run2) {
                 if constexpr (P > 0) pass2<P>(s, nch);
                 __syncthreads();
-                if (tid < nch && s.cs[tid].n > 0) after_pass2(s.cs[tid], P, p.counters);
             }
+            if (tid < nch && s.cs[tid].n > 0) {
+                ChanState &cs = s.cs[tid];
+                if (run2) after_pass2(cs, P, p.counters);
+                cs.ex_cand = next_open_candidate(cs, prune, p.counters);
+                cs.ex_s = 0; cs.ex_max = 0;
+            }
+            __syncthreads();
             // exact evaluation of whatever is still open (bounded candidates that can still win)
             for (;;) {
-                __syncthreads();
-                if (tid == 0) s.more = 0;
-                __syncthreads();
-                if (tid < nch && s.cs[tid].n > 0) {
-                    ChanState &cs = s.cs[tid];
-                    cs.ex_cand = next_open_candidate(cs, prune, p.counters);
-                    cs.ex_s = 0; cs.ex_max = 0;
-                    if (cs.ex_cand >= 0) atomicOr(reinterpret_cast<u32 *>(&s.more), 1u);
-                }
-                __syncthreads();
-                if (!s.more) break;
+                bool more = false;
+                for (int q = 0; q < nch; q++) more |= s.cs[q].n > 0 && s.cs[q].ex_cand >= 0;
+                if (!more) break;
                 if (tid == 0) atomicAdd(p.counters + 1, 1u);
                 pass3<P>(s, nch);
                 __syncthreads();
-                if (tid < nch && s.cs[tid].n > 0) after_pass3(s.cs[tid]);
+                if (tid < nch && s.cs[tid].n > 0) {
+                    ChanState &cs = s.cs[tid];
+                    after_pass3(cs);
+                    cs.ex_cand = next_open_candidate(cs, prune, p.counters);
+                    cs.ex_s = 0; cs.ex_max = 0;
+                }
+                __syncthreads();
             }
             // encode_channel_int, encoder.rs:184-216: strictly smaller wins, candidates in order
             if (tid < nch) {

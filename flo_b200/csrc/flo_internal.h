@@ -8,7 +8,10 @@
 
 namespace flo {
 
-constexpr int NT = 512;               // threads per CTA of the frame-encode kernel
+#ifndef FLO_NT
+#define FLO_NT 512
+#endif
+constexpr int NT = FLO_NT;            // threads per CTA of the frame-encode kernel
 constexpr int NWARP = NT / 32;
 constexpr int CH = 16;                // samples per thread chunk
 constexpr int RING_WORDS = 4096;      // bit-packer staging ring (16 KB)

@@ -35,8 +35,8 @@ typedef int32_t i32;
 // ----------------------------------------------------------------------------
 __constant__ u32 c_crc_slice[4][256];   // slice-by-4 tables of the reflected CRC-32 (crc32.rs:2-20)
 __constant__ u32 c_x2n[32];             // x^(2^i) mod p, reflected (for crc combine)
-__constant__ u32 c_pow128[33];          // x^(8*128*j) mod p, j = 0..32
-__constant__ u32 c_powseg;              // x^(8*CRC_SEG) mod p
+__constant__ u32 c_xop[4][256];         // v -> v * x^1024 mod p, by byte of v (strided Horner step of the CRC kernel)
+__constant__ u32 c_klane[32];           // x^(32 (32 - lane)) mod p
 
 static u32 h_multmodp(u32 a, u32 b) {
     u32 m = 1u << 31, p = 0;
@@ -66,13 +66,16 @@ void upload_crc_tables() {
     u32 p = 1u << 30;                      // x^1
     h_x2n[0] = p;
     for (int n = 1; n < 32; n++) h_x2n[n] = p = h_multmodp(p, p);
-    u32 pow128[33];
-    for (int j = 0; j <= 32; j++) pow128[j] = h_x2nmodp((u64)128 * j, 3);
-    u32 powseg = h_x2nmodp(CRC_SEG, 3);
+    static u32 xop[4][256];
+    const u32 x1024 = h_x2nmodp(128, 3);
+    for (int b = 0; b < 4; b++)
+        for (u32 t = 0; t < 256; t++) xop[b][t] = h_multmodp(x1024, t << (8 * b));
+    u32 klane[32];
+    for (int l = 0; l < 32; l++) klane[l] = h_x2nmodp(4 * (32 - l), 3);
     cudaMemcpyToSymbol(c_crc_slice, slice, sizeof slice);
     cudaMemcpyToSymbol(c_x2n, h_x2n, sizeof h_x2n);
-    cudaMemcpyToSymbol(c_pow128, pow128, sizeof pow128);
-    cudaMemcpyToSymbol(c_powseg, &powseg, sizeof powseg);
+    cudaMemcpyToSymbol(c_xop, xop, sizeof xop);
+    cudaMemcpyToSymbol(c_klane, klane, sizeof klane);
 }
 
 __device__ __forceinline__ u32 multmodp(u32 a, u32 b) {
@@ -131,17 +134,19 @@ __global__ void k_write_toc(const FinalParams p) {
     put_u32le(e + 16, (u32)ts);
 }
 
-// CRC-32 of one 128-byte aligned-by-construction block given as bytes [a, a+128) of buf
-__device__ __forceinline__ u32 crc_update_word(u32 c, u32 w, const u32 (*T)[256]) {
-    c ^= w;
-    return T[3][c & 0xff] ^ T[2][(c >> 8) & 0xff] ^ T[1][(c >> 16) & 0xff] ^ T[0][c >> 24];
-}
-
-// One warp per 64 KB segment of a track's DATA chunk (crc32.rs:23-30 restated as
-// per-block CRCs combined with x^(8 len) shifts; result identical to the serial loop).
+// CRC-32 (crc32.rs:2-30) of a track's DATA chunk, one warp per 64 KB segment.
+//
+// Works on the raw CRC R(M) = M(x) x^32 mod p (zero initial state, no final complement), which is
+// linear: R(A || B) = R(A) x^(8|B|) ^ R(B), and leading zero bytes are free.  The reference's value is
+// crc(M) = ~(R(M) ^ 0xFFFFFFFF x^(8|M|)) (k_write_headers).  Inside a segment lane l takes the
+// aligned words l, l+32, l+64, ... (coalesced loads) counted so that the last word falls on lane 31,
+// and runs the Horner step d = d x^1024 ^ w -- four table look-ups, like an ordinary slice-by-4 step.
+// Lane l's stream then weighs x^(32 (32 - l)); the XOR over the lanes is the state after the last
+// whole word, and the <= 3 bytes behind it are added with the byte-wise step.  The segment's R is
+// shifted by the bytes that follow it in the track and XORed into the track's accumulator.
 __global__ void __launch_bounds__(CRC_NT) k_crc_segments(const FinalParams p) {
-    __shared__ u32 T[4][256];
-    for (int i = threadIdx.x; i < 1024; i += CRC_NT) (&T[0][0])[i] = (&c_crc_slice[0][0])[i];
+    __shared__ u32 X[4][256];
+    for (int i = threadIdx.x; i < 1024; i += CRC_NT) (&X[0][0])[i] = (&c_xop[0][0])[i];
     __syncthreads();
     const u32 lane = threadIdx.x & 31;
     const u32 seg = (blockIdx.x * CRC_NT + threadIdx.x) >> 5;
@@ -157,45 +162,36 @@ __global__ void __launch_bounds__(CRC_NT) k_crc_segments(const FinalParams p) {
     const u64 soff = (u64)(seg - tr.first_seg) * CRC_SEG;
     if (soff >= dsize) return;
     const u64 d0 = tr.static_off + e0 + FILE_HDR + 4 + 20ull * tr.n_frames;
-    const uint8_t *base = p.out + d0 + soff;
-    const u32 slen = (u32)min((u64)CRC_SEG, dsize - soff);
-    const u32 nblk = slen >> 7;                      // full 128-byte blocks
-    const u32 mis = (u32)((uintptr_t)base & 3u);
-    const u32 *wbase = reinterpret_cast<const u32 *>(base - mis);
-    u32 crc = 0;                                     // crc("") = 0 is the identity of combine
-    for (u32 b0 = 0; b0 < nblk; b0 += 32) {
-        const u32 m = min(32u, nblk - b0);
-        u32 c = 0;
-        if (lane < m) {
-            const u32 *w = wbase + (size_t)(b0 + lane) * 32;
-            u32 r = 0xFFFFFFFFu;
-            if (mis == 0) {
-#pragma unroll 8
-                for (int i = 0; i < 32; i++) r = crc_update_word(r, w[i], T);
-            } else {
-                u32 cur = w[0];
-#pragma unroll 8
-                for (int i = 0; i < 32; i++) {
-                    const u32 nxt = w[i + 1];
-                    r = crc_update_word(r, __funnelshift_r(cur, nxt, 8 * mis), T);
-                    cur = nxt;
-                }
+    const u64 a = d0 + soff;                                 // byte range [a, b) of p.out (p.out is 16-byte aligned)
+    const u64 b = a + min((u64)CRC_SEG, dsize - soff);
+    const u64 b4 = b & ~3ull;
+    u32 c = 0;
+    u64 tail = a;
+    if (b4 > a) {
+        const u64 a4 = a & ~3ull;
+        const u64 nwords = (b4 - a4) >> 2;
+        const u64 J = (nwords + 31) >> 5;
+        const i64 s0 = (i64)b4 - (i64)(128 * J);             // may lie before a4: those words count as zero
+        const u32 head_mask = 0xFFFFFFFFu << (8 * (u32)(a - a4));
+        u32 d = 0;
+        i64 addr = s0 + 4 * (i64)lane;
+        for (u64 j = 0; j < J; j++, addr += 128) {
+            u32 w = 0;
+            if (addr >= (i64)a4) {
+                w = __ldg(reinterpret_cast<const u32 *>(p.out + addr));
+                if (addr == (i64)a4) w &= head_mask;
             }
-            c = ~r;
-            c = multmodp(c_pow128[m - 1 - lane], c);
+            d = X[0][d & 0xff] ^ X[1][(d >> 8) & 0xff] ^ X[2][(d >> 16) & 0xff] ^ X[3][d >> 24] ^ w;
         }
+        c = multmodp(c_klane[lane], d);
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) c ^= __shfl_xor_sync(0xffffffffu, c, o);
-        crc = multmodp(c_pow128[m], crc) ^ c;
+        tail = b4;
     }
     if (lane == 0) {
-        u32 r = ~crc;
-        for (u32 i = nblk << 7; i < slen; i++) r = (r >> 8) ^ T[0][(r ^ base[i]) & 0xff];
-        // crc(A || B) = crc(A) * x^(8 |B|) ^ crc(B)  (mod p): shift this segment's CRC by the bytes behind it
-        // and fold it into the track's CRC; XOR makes the order of the segments irrelevant.
-        const u64 after = dsize - (soff + slen);
-        const u32 shifted = after ? multmodp(x2nmodp(after, 3), ~r) : ~r;
-        atomicXor(&p.track_crc[lo], shifted);
+        for (u64 i = tail; i < b; i++) c = (c >> 8) ^ c_crc_slice[0][(c ^ p.out[i]) & 0xff];
+        const u64 after = (d0 + dsize) - b;
+        atomicXor(&p.track_crc[lo], multmodp(x2nmodp(after, 3), c));
     }
 }
 
@@ -209,7 +205,8 @@ __global__ void k_write_headers(const FinalParams p) {
     const u64 toc_size = 4 + 20ull * tr.n_frames;
     uint8_t *o = p.out + file0;
     if (threadIdx.x == 0) {
-        const u32 crc = p.track_crc[t];
+        // crc(M) = ~(R(M) ^ 0xFFFFFFFF x^(8 |M|)): initial state and final complement of crc32.rs:24-29
+        const u32 crc = ~(p.track_crc[t] ^ multmodp(x2nmodp(dsize, 3), 0xFFFFFFFFu));
         o[0] = 0x46; o[1] = 0x4C; o[2] = 0x4F; o[3] = 0x21;        // "FLO!", types.rs:6
         o[4] = 1; o[5] = 2;                                        // version 1.2, types.rs:12-13
         o[6] = 0; o[7] = 0;                                        // flags: lossless
