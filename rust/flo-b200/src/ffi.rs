@@ -1,0 +1,63 @@
+//! Raw bindings of include/flo_b200.h (one declaration per exported symbol).
+#![allow(non_camel_case_types)]
+use std::os::raw::{c_char, c_int, c_void};
+
+#[repr(C)]
+pub struct flo_ctx {
+    _private: [u8; 0],
+}
+
+#[repr(C)]
+pub struct flo_track {
+    pub samples: *const c_void,
+    pub n_interleaved: usize,
+    pub sample_rate: u32,
+    pub channels: u8,
+    pub bit_depth: u8,
+    pub meta: *const u8,
+    pub meta_len: usize,
+}
+
+#[repr(C)]
+pub struct flo_out {
+    pub data: *mut u8,
+    pub len: usize,
+}
+
+#[repr(C)]
+pub struct flo_cand_report {
+    pub k: i32,
+    pub pad: i32,
+    pub size: i64,
+}
+
+pub const FLO_FMT_F32: c_int = 0;
+pub const FLO_FMT_PCM16: c_int = 1;
+
+extern "C" {
+    pub fn flo_ctx_create(device: c_int, out: *mut *mut flo_ctx) -> c_int;
+    pub fn flo_ctx_destroy(ctx: *mut flo_ctx);
+    pub fn flo_encode(ctx: *mut flo_ctx, samples: *const f32, n_interleaved: usize, sample_rate: u32,
+                      channels: u8, bit_depth: u8, level: u8, meta: *const u8, meta_len: usize,
+                      out: *mut *mut u8, out_len: *mut usize) -> c_int;
+    pub fn flo_encode_pcm16(ctx: *mut flo_ctx, pcm: *const i16, n_interleaved: usize, sample_rate: u32,
+                            channels: u8, bit_depth: u8, level: u8, meta: *const u8, meta_len: usize,
+                            out: *mut *mut u8, out_len: *mut usize) -> c_int;
+    pub fn flo_encode_batch(ctx: *mut flo_ctx, tracks: *const flo_track, n_tracks: usize, format: c_int,
+                            level: u8, outs: *mut flo_out) -> c_int;
+    pub fn flo_encode_batch_device(ctx: *mut flo_ctx, tracks: *const flo_track, n_tracks: usize, format: c_int,
+                                   level: u8, d_out: *mut c_void, d_out_capacity: usize,
+                                   offsets: *mut u64, lens: *mut u64) -> c_int;
+    pub fn flo_output_bound(tracks: *const flo_track, n_tracks: usize) -> usize;
+    pub fn flo_ctx_set_stream(ctx: *mut flo_ctx, cuda_stream: *mut c_void) -> c_int;
+    pub fn flo_ctx_last_timing(ctx: *mut flo_ctx, ms: *mut f32, launches: *mut u32) -> c_int;
+    pub fn flo_ctx_last_counters(ctx: *mut flo_ctx, out: *mut u64) -> c_int;
+    pub fn flo_ctx_enable_report(ctx: *mut flo_ctx, enable: c_int) -> c_int;
+    pub fn flo_ctx_read_report(ctx: *mut flo_ctx, frame: u32, channel: u32, out: *mut flo_cand_report) -> c_int;
+    pub fn flo_host_alloc(bytes: usize) -> *mut c_void;
+    pub fn flo_host_free(p: *mut c_void);
+    pub fn flo_free(p: *mut c_void);
+    pub fn flo_last_error() -> *const c_char;
+    pub fn flo_version() -> *const c_char;
+    pub fn flo_device_count() -> c_int;
+}
