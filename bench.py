@@ -52,7 +52,7 @@ class ClockSampler:
     def start(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}",
-                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                          "--format=csv,noheader,nounits", "-lms", "20"],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             threading.Thread(target=self._read, daemon=True).start()
         except Exception:
@@ -60,16 +60,23 @@ class ClockSampler:
 
     def _read(self):
         for line in self.proc.stdout:
-            self.rows.append(line.strip())
+            self.rows.append((time.perf_counter(), line.strip()))
 
-    def stop(self) -> dict:
+    def stop(self, t0: float = 0.0, t1: float = float("inf")) -> dict:
+        """Summary of the samples taken inside [t0, t1] (the timed region); if the region was shorter than
+        the sampling period, of the samples since `t0 - 1 s` (warm-up steps of the same workload)."""
         if self.proc is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        time.sleep(0.15)
+        time.sleep(0.05)
         self.proc.terminate()
+        inside = [r for t, r in self.rows if t0 <= t <= t1]
+        window = "timed region"
+        if len(inside) < 3:
+            inside = [r for t, r in self.rows if t0 - 1.0 <= t <= t1 + 0.05]
+            window = "timed region + preceding warm-up (region shorter than the sampling period)"
         sm, mx, reasons = [], None, set()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for r in self.rows:
+        for r in inside:
             p = [x.strip() for x in r.split(",")]
             if len(p) < 7:
                 continue
@@ -81,7 +88,8 @@ class ClockSampler:
                 if v.lower().startswith("active"):
                     reasons.add(nme)
         sm.sort()
-        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": mx, "reasons": sorted(reasons), "samples": len(sm)}
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": mx, "reasons": sorted(reasons),
+                "samples": len(sm), "window": window}
 
 
 def host_threads() -> int:
@@ -123,6 +131,7 @@ def main() -> int:
     ap.add_argument("--cpu-sample-seconds", type=int, default=0, help="0 = auto (about 15 s of CPU work)")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-extras", action="store_true", help="skip the per-level / PCM16-entry side measurements")
     args = ap.parse_args()
     level = args.level
 
@@ -184,6 +193,9 @@ def main() -> int:
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
     ctx = flo_b200.Context(local_rank)
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()              # 20 ms period; the summary only uses samples inside the timed region
     stream = torch.cuda.current_stream()
     ctx.set_stream(stream.cuda_stream)
 
@@ -215,13 +227,11 @@ def main() -> int:
             dist.barrier()
         torch.cuda.synchronize()
 
-    for _ in range(max(args.warmup, 3)):
+    for i in range(max(args.warmup, 3)):
         off, ln = step()
     out_bytes = int(ln.sum())
     sync_all()
-    sampler = ClockSampler(local_rank)
-    if rank == 0:
-        sampler.start()
+    t_region0 = time.perf_counter()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     enc_ms, dev_ms, launches = [], [], 0
     ev0.record()
@@ -231,7 +241,7 @@ def main() -> int:
         enc_ms.append(t["encode_ms"]); dev_ms.append(t["device_ms"]); launches += t["launches"]
     ev1.record()
     sync_all()
-    clocks = sampler.stop() if rank == 0 else None
+    clocks = sampler.stop(t_region0, time.perf_counter()) if rank == 0 else None
     counters = ctx.last_counters()
     ms_total = ev0.elapsed_time(ev1)
     tmax = torch.tensor([ms_total], dtype=torch.float64, device=dev)
@@ -249,6 +259,27 @@ def main() -> int:
                 "algorithmic_bytes_per_launch": alg_bytes,
                 "note": "integer-ALU/FP64-pipe bound at level 5 (10 exhaustive candidates per channel), see DESIGN.md"}
 
+    # side measurements (not the headline): other compression levels and the PCM16 entry, same stream
+    extras = None
+    if world == 1 and not args.no_extras:
+        extras = {"note": "encode-kernel ms per step and % of measured HBM peak on the same 1-hour stream; "
+                          "levels 0-3 try fixed predictors only (encoder.rs:204)", "levels": {}}
+        for lv in (0, 2, 4, 5, 7, 9):
+            ts = []
+            for _ in range(3):
+                o2, l2 = ctx.encode_batch_device(ptrs, n_list, [SR], [CH], [16], d_out.data_ptr(), bound, level=lv)
+                ts.append(ctx.last_timing()["encode_ms"])
+            ab = 4.0 * total_inter + float(l2.sum())
+            extras["levels"][str(lv)] = {"kernel_ms": min(ts), "flo_bytes": int(l2.sum()),
+                                         "pct_of_hbm_peak": 100.0 * ab / (min(ts) * 1e-3) / 1e9 / peak}
+        ts = []
+        for _ in range(3):
+            o2, l2 = ctx.encode_batch_device([pcm_tracks[0].data_ptr()], n_list, [SR], [CH], [16], d_out.data_ptr(), bound,
+                                             level=level, fmt=flo_b200.FMT_PCM16)
+            ts.append(ctx.last_timing()["encode_ms"])
+        extras["pcm16_entry"] = {"kernel_ms": min(ts), "same_bytes_as_f32_entry": int(l2.sum()) == out_bytes,
+                                 "pct_of_hbm_peak": 100.0 * (2.0 * total_inter + float(l2.sum())) / (min(ts) * 1e-3) / 1e9 / peak}
+
     # e2e: host buffers through the reference-facing C-ABI call (H2D + D2H inside the timed region)
     e2e = None
     if not args.no_e2e:
@@ -257,13 +288,16 @@ def main() -> int:
             h.copy_(d)
         torch.cuda.synchronize()
         specs = [flo_b200.TrackSpec(h.numpy(), SR, CH, 16, b"") for h in host_in]
-        outs = ctx.encode_batch(specs, level)                      # warm-up (arena growth, page faults)
-        e2e_out = sum(len(o) for o in outs)
+        for _ in range(2):                                         # warm-up (arena growth, pinned output pool)
+            with ctx.encode_batch(specs, level, views=True) as res:
+                e2e_out = res.total_bytes()
         sync_all()
         t0 = time.perf_counter()
-        reps = max(1, min(args.steps, 3))
+        reps = max(1, min(args.steps, 5))
         for _ in range(reps):
-            outs = ctx.encode_batch(specs, level)
+            # the call returns when the .flo images are in host memory; they are read (first/last byte) and released
+            with ctx.encode_batch(specs, level, views=True) as res:
+                assert all(a[0] == 0x46 and a[-1] is not None for a in res.arrays)
         torch.cuda.synchronize()
         dt = (time.perf_counter() - t0) / reps
         tm = torch.tensor([dt], dtype=torch.float64, device=dev)
@@ -272,7 +306,7 @@ def main() -> int:
         e2e = {"value": 2.0 * total_inter * world / float(tm.item()) / 1e9, "unit": "GB/s",
                "h2d_bytes_per_step": 4 * total_inter, "d2h_bytes_per_step": e2e_out,
                "ms_per_step": float(tm.item()) * 1e3, "x_realtime": seconds * world / float(tm.item())}
-        del host_in, specs, outs
+        del host_in, specs
 
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu:
@@ -292,7 +326,8 @@ def main() -> int:
                 "pct_of_hbm_peak": 100.0 * achieved / peak, "flo_bytes_per_step_per_gpu": out_bytes,
                 "compression_ratio": 2.0 * total_inter / out_bytes, "roofline": roofline, "cpu_baseline": cpu,
                 "e2e": e2e, "gpu_launches": launches, "clocks": clocks,
-                "device_ms_per_step": sum(dev_ms) / len(dev_ms), "analysis_counters_last_step": counters}
+                "device_ms_per_step": sum(dev_ms) / len(dev_ms), "analysis_counters_last_step": counters,
+                "extras": extras}
         print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()

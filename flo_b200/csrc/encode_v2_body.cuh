@@ -665,47 +665,78 @@ __device__ __forceinline__ void chunk_codes(const ChanState &cs, int i0, const d
     });
 }
 
+// Appends the codes of one chunk to the staging ring, MSB first (BitWriter, rice.rs:162-208).
+// Branch-free in the common case: every sample shifts its code into a 64-bit accumulator and a
+// predicated store drops a 32-bit word whenever one is complete.  Words that only this thread
+// writes are stored plainly; its first word (shared with the preceding threads) is kept in a
+// register and OR-ed in at the end together with the last, partial word.
 template <bool WINDOWED, bool MASKED>
 __device__ __forceinline__ void emit_chunk(u32 *ring, const u32 (&u)[CH], int nv, int k, bool raw, u64 start,
                                            u32 wlo, u32 whi) {
-    u32 w = (u32)(start >> 5);
-    int nb = (int)(start & 31);
+    const u32 w0 = (u32)(start >> 5);
+    u32 w = w0;
+    int nb = (int)(start & 31);                    // leading zero bits stand for the part of w0 that is not ours
     u64 acc = 0;
-    bool firstw = true;
-    auto out = [&](u32 word) {
-        if (!WINDOWED || (w >= wlo && w < whi)) {
-            if (firstw) atomicOr(&ring[w & (RING_WORDS - 1)], word);
-            else ring[w & (RING_WORDS - 1)] = word;
-        }
-        firstw = false;
-        w++;
-    };
-    auto put = [&](u32 v, int len) {
+    u32 head = 0;
+    auto put = [&](u32 v, int len) {               // 1 <= len <= 32, v < 2^len
         acc = (acc << len) | v;
         nb += len;
-        if (nb >= 32) { out((u32)(acc >> (nb - 32))); nb -= 32; }
+        const bool full = nb >= 32;
+        const u32 word = (u32)(acc >> ((nb - 32) & 63));
+        const bool mine = full && w != w0 && (!WINDOWED || (w >= wlo && w < whi));
+        if (mine) ring[w & (RING_WORDS - 1)] = word;
+        head = (full && w == w0) ? word : head;
+        w += full ? 1u : 0u;
+        nb -= full ? 32 : 0;
     };
+    const u32 kmask = (1u << k) - 1u;
+    // Taken branches stall instruction fetch, so the per-sample code is straight-line: raw and Rice have
+    // separate loops, and quotients above 16 (codes longer than 32 bits) are detected once per chunk.
+    if (raw) {
 #pragma unroll
-    for (int j = 0; j < CH; j++) {
-        if (!MASKED || j < nv) {
-            if (raw) {
-                put(u[j], 16);
-            } else {                               // encode_sample, rice.rs:94-114
-                u32 q = u[j] >> k;
-                u32 rem = u[j] & ((1u << k) - 1u);
-                if (q <= 16) {
-                    put((((1u << q) - 1u) << (k + 1)) | rem, (int)q + k + 1);
-                } else {
-                    while (q > 0) { u32 t = q < 24 ? q : 24; put((1u << t) - 1u, (int)t); q -= t; }
-                    put(rem, k + 1);
+        for (int j = 0; j < CH; j++)
+            if (!MASKED || j < nv) put(u[j], 16);
+    } else {
+        u32 qmax = 0;
+#pragma unroll
+        for (int j = 0; j < CH; j++) qmax = max(qmax, (!MASKED || j < nv) ? (u[j] >> k) : 0u);
+        if (qmax <= 16) {
+#pragma unroll
+            for (int j = 0; j < CH; j++) {             // encode_sample, rice.rs:94-114
+                if (!MASKED || j < nv) {
+                    const u32 q = u[j] >> k;
+                    put((((1u << q) - 1u) << (k + 1)) | (u[j] & kmask), (int)q + k + 1);
                 }
+            }
+        } else {
+#pragma unroll 1
+            for (int j = 0; j < (MASKED ? nv : CH); j++) {
+                u32 uj = u[0];
+#pragma unroll
+                for (int t = 1; t < CH; t++) uj = (t == j) ? u[t] : uj;
+                u32 q = uj >> k;
+                while (q > 16) { const u32 t = q < 24 ? q : 24; put((1u << t) - 1u, (int)t); q -= t; }
+                put((((1u << q) - 1u) << (k + 1)) | (uj & kmask), (int)q + k + 1);
             }
         }
     }
-    if (nb > 0) {
-        u32 word = (u32)(acc << (32 - nb));
-        if (!WINDOWED || (w >= wlo && w < whi)) atomicOr(&ring[w & (RING_WORDS - 1)], word);
+    const u32 tailw = nb > 0 ? (u32)(acc << (32 - nb)) : 0u;
+    const bool in0 = !WINDOWED || (w0 >= wlo && w0 < whi);
+#ifdef NO_ATOMIC_TEST
+    if (w == w0) {
+        if (in0 && tailw) ring[w0 & (RING_WORDS - 1)] = tailw;
+    } else {
+        if (in0 && head) ring[w0 & (RING_WORDS - 1)] = head;
+        if (tailw && (!WINDOWED || (w >= wlo && w < whi))) ring[w & (RING_WORDS - 1)] = tailw;
     }
+#else
+    if (w == w0) {
+        if (in0 && tailw) atomicOr(&ring[w0 & (RING_WORDS - 1)], tailw);
+    } else {
+        if (in0 && head) atomicOr(&ring[w0 & (RING_WORDS - 1)], head);
+        if (tailw && (!WINDOWED || (w >= wlo && w < whi))) atomicOr(&ring[w & (RING_WORDS - 1)], tailw);
+    }
+#endif
 }
 
 // Copy completed ring words [wa, wb) to the output and clear them.  Word w of the ring maps
@@ -729,7 +760,8 @@ __device__ __forceinline__ void flush_ring(u32 *ring, uint8_t *obase, u64 abase,
 // Pack one channel's residual payload at byte offset `pos` (relative to obase, which is 4-byte
 // aligned) -- encode_i32 / BitWriter (rice.rs:84-92, 162-208) or encode_raw (encoder.rs:220-226).
 template <int P>
-__device__ void pack_channel(Smem &s, const ChanState &cs, const ChanResult &cr, uint8_t *obase, u64 pos, u32 *err) {
+__device__ void pack_channel(Smem &s, const ChanState &cs, const ChanResult &cr, uint8_t *obase, u64 pos, u32 *err,
+                             unsigned long long *phase) {
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
     const int n = cs.n;
     const int mode = cr.kind == 0 ? 13 : cr.order;
@@ -743,6 +775,7 @@ __device__ void pack_channel(Smem &s, const ChanState &cs, const ChanResult &cr,
     const int nsc = (n + per_sc - 1) / per_sc;
     const double *qd = s.wqd;
     for (int sc = 0; sc < nsc; sc++) {
+        const long long pk0 = clock64();
         const int i0 = sc * per_sc + tid * CH;
         const bool last = sc == nsc - 1;               // only the last super-chunk has short or absent chunks
         const int nv = last ? max(0, min(CH, n - i0)) : CH;
@@ -778,6 +811,7 @@ __device__ void pack_channel(Smem &s, const ChanState &cs, const ChanResult &cr,
                     if (j < nv) tb += (u[j] >> k) + 1u + (u32)k;
             }
         }
+        const long long pk1 = clock64();
         // block exclusive scan of the chunk bit counts: warp scan, one barrier, then every warp scans the
         // 16 warp totals itself.  The totals are double buffered by round parity, and the ring words flushed
         // in the previous round are only touched again behind this round's barrier.
@@ -799,6 +833,7 @@ __device__ void pack_channel(Smem &s, const ChanState &cs, const ChanResult &cr,
         }
         const u32 warp_excl = __shfl_sync(0xffffffffu, wincl - wv, wid);
         const u32 scan_total = __shfl_sync(0xffffffffu, wincl, NWARP - 1);
+        const long long pk2 = clock64();
         const u64 start = bitpos + warp_excl + (inc - tb);
         const u64 end_sc = bitpos + scan_total;
         const u32 wlast = (u32)((end_sc + 31) >> 5);
@@ -808,6 +843,7 @@ __device__ void pack_channel(Smem &s, const ChanState &cs, const ChanResult &cr,
             if (!last) emit_chunk<false, false>(s.ring, u, CH, k, raw, start, 0, 0);
             else if (nv > 0) emit_chunk<false, true>(s.ring, u, nv, k, raw, start, 0, 0);
             __syncthreads();
+            if (tid == 0) { const long long pk3 = clock64(); atomicAdd(phase + 5, (u64)(pk1 - pk0)); atomicAdd(phase + 6, (u64)(pk2 - pk1)); atomicAdd(phase + 7, (u64)(pk3 - pk2)); }
             const u32 wend = (u32)(end_sc >> 5);
             flush_ring(s.ring, obase, abase, lo, hi, wlo, wend);
             wlo = wend;
@@ -1053,6 +1089,7 @@ __global__ void __launch_bounds__(NT, 1) k_encode_frames(const EncodeParams p) {
         __syncthreads();
         const u32 g = s.g;
         if (g >= p.n_frames) break;
+        const long long tc0 = clock64();
         const uint2 fd = p.frames[g];
         const TrackDev tr = p.tracks[fd.x];
         const u32 C = tr.channels;
@@ -1095,6 +1132,7 @@ __global__ void __launch_bounds__(NT, 1) k_encode_frames(const EncodeParams p) {
             continue;
         }
 
+        const long long tc1 = clock64();
         if (tid == 0) atomicAdd(p.counters, 1u);
         // mid/side decision, encoder.rs:94-100, 131-153
         int ms = 0;
@@ -1200,6 +1238,7 @@ __global__ void __launch_bounds__(NT, 1) k_encode_frames(const EncodeParams p) {
         }
         __syncthreads();
 
+        const long long tc2 = clock64();
         // frame typing and size, encoder.rs:102-127, types.rs:242-267
         bool all_raw = true;
         u32 fsize = 6;
@@ -1216,6 +1255,7 @@ __global__ void __launch_bounds__(NT, 1) k_encode_frames(const EncodeParams p) {
         }
         __syncthreads();
 
+        const long long tc3 = clock64();
         // write the frame, writer.rs:236-301
         const u64 fpos = data_base + s.frame_excl;
         uint8_t *o = p.out;
@@ -1252,9 +1292,15 @@ __global__ void __launch_bounds__(NT, 1) k_encode_frames(const EncodeParams p) {
                     if (r.kind != 0) *h++ = (uint8_t)r.k;
                 }
             }
-            if (r.kind != 3 && r.nbytes > 0) pack_channel<P>(s, s.cs[0], r, o, pos + 4 + hdr, p.err);
+            if (r.kind != 3 && r.nbytes > 0) pack_channel<P>(s, s.cs[0], r, o, pos + 4 + hdr, p.err, p.phase_cycles);
             pos += 4 + hdr + r.nbytes;
         }
         if (tid == 0 && pos - fpos != fsize) atomicExch(p.err, 0xBAD00002u);
+        if (tid == 0) {
+            const long long tc4 = clock64();
+            atomicAdd(p.phase_cycles + 0, (u64)(tc1 - tc0)); atomicAdd(p.phase_cycles + 1, (u64)(tc2 - tc1));
+            atomicAdd(p.phase_cycles + 2, (u64)(tc3 - tc2)); atomicAdd(p.phase_cycles + 3, (u64)(tc4 - tc3));
+            atomicAdd(p.phase_cycles + 4, (u64)(tc4 - tc0));
+        }
     }
 }

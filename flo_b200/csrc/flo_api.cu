@@ -26,7 +26,6 @@ static void set_err(const char *fmt, ...) {
 }
 extern "C" const char *flo_last_error(void) { return g_err; }
 extern "C" const char *flo_version(void) { return "flo_b200 0.1 (sm_100a)"; }
-extern "C" void flo_free(void *p) { free(p); }
 
 #define CK(expr)                                                                           \
     do {                                                                                   \
@@ -90,7 +89,71 @@ struct HostBuf {                      // grow-only pinned host arena
 
 inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 
+// Pinned output blocks.  Large results are copied device -> host straight into one page-locked block
+// and handed out as pointers into it (no second host copy); flo_free() on the last pointer of a
+// block returns it to a small process-wide pool for the next call.
+struct OutBlock {
+    uint8_t *base = nullptr;
+    size_t cap = 0;
+    size_t refs = 0;
+};
+std::mutex g_blocks_mu;
+std::vector<OutBlock *> g_live;       // handed out, refs > 0
+std::vector<OutBlock *> g_pool;       // free, reusable
+constexpr size_t POOL_MAX_BLOCKS = 4;
+constexpr size_t SMALL_OUTPUT = 1u << 20;
+
+OutBlock *take_block(size_t bytes) {
+    std::lock_guard<std::mutex> lk(g_blocks_mu);
+    size_t best = g_pool.size();
+    for (size_t i = 0; i < g_pool.size(); i++)
+        if (g_pool[i]->cap >= bytes && (best == g_pool.size() || g_pool[i]->cap < g_pool[best]->cap)) best = i;
+    if (best < g_pool.size()) {
+        OutBlock *b = g_pool[best];
+        g_pool.erase(g_pool.begin() + best);
+        return b;
+    }
+    OutBlock *b = new (std::nothrow) OutBlock();
+    if (!b) return nullptr;
+    const size_t cap = bytes + bytes / 8 + 4096;
+    if (cudaMallocHost((void **)&b->base, cap) != cudaSuccess) { cudaGetLastError(); delete b; return nullptr; }
+    b->cap = cap;
+    return b;
+}
+void publish_block(OutBlock *b, size_t refs) {
+    std::lock_guard<std::mutex> lk(g_blocks_mu);
+    b->refs = refs;
+    g_live.push_back(b);
+}
+void recycle_block_locked(OutBlock *b) {
+    if (g_pool.size() < POOL_MAX_BLOCKS) { g_pool.push_back(b); return; }
+    cudaFreeHost(b->base);
+    delete b;
+}
+void drop_block(OutBlock *b) {          // never published (error path)
+    std::lock_guard<std::mutex> lk(g_blocks_mu);
+    recycle_block_locked(b);
+}
+
 }  // namespace
+
+extern "C" void flo_free(void *p) {
+    if (!p) return;
+    {
+        std::lock_guard<std::mutex> lk(g_blocks_mu);
+        for (size_t i = 0; i < g_live.size(); i++) {
+            OutBlock *b = g_live[i];
+            if ((uint8_t *)p >= b->base && (uint8_t *)p < b->base + b->cap) {
+                if (--b->refs == 0) {
+                    g_live.erase(g_live.begin() + i);
+                    recycle_block_locked(b);
+                }
+                return;
+            }
+        }
+    }
+    free(p);
+}
 
 struct flo_ctx {
     int device = 0;
@@ -100,7 +163,7 @@ struct flo_ctx {
     cudaStream_t own_stream = nullptr, stream = nullptr;
     cudaEvent_t ev[8] = {};
     DevBuf in, out, meta, tracks, frames, ctrl, fexcl, fsize, foff, plane, cres, report;
-    uint64_t counters[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    uint64_t counters[16] = {0};      // [0..7] analysis counters, [8..15] per-phase SM clock sums
     HostBuf h_small, h_out;
     bool report_on = false;
     uint32_t report_frames = 0;
@@ -170,7 +233,7 @@ extern "C" int flo_ctx_last_timing(flo_ctx *c, float ms[6], uint32_t *launches) 
     return FLO_OK;
 }
 
-extern "C" int flo_ctx_last_counters(flo_ctx *c, uint64_t out[8]) {
+extern "C" int flo_ctx_last_counters(flo_ctx *c, uint64_t out[16]) {
     if (!c || !out) { set_err("bad argument"); return FLO_ERR_ARG; }
     std::lock_guard<std::mutex> lk(c->mu);
     memcpy(out, c->counters, sizeof c->counters);
@@ -295,13 +358,13 @@ static int encode_batch_impl(flo_ctx *c, const flo_track *tracks, size_t n_track
     const uint32_t NF = (uint32_t)L.n_frames, NSEG = (uint32_t)L.n_segs, NTR = (uint32_t)n_tracks;
     if ((rc = c->tracks.reserve(sizeof(TrackDev) * n_tracks))) return rc;
     if ((rc = c->frames.reserve(sizeof(uint2) * std::max<uint64_t>(NF, 1)))) return rc;
-    const size_t ctrl_bytes = 8ull * NF + 64 + 4ull * n_tracks;        // status words, ticket, err, counters, track CRCs
+    const size_t ctrl_bytes = 8ull * NF + 128 + 4ull * n_tracks;       // status words, ticket, err, counters, phase clocks, track CRCs
     if ((rc = c->ctrl.reserve(ctrl_bytes))) return rc;
     if ((rc = c->fexcl.reserve(8ull * std::max<uint64_t>(NF, 1)))) return rc;
     if ((rc = c->fsize.reserve(4ull * std::max<uint64_t>(NF, 1)))) return rc;
     if ((rc = c->foff.reserve(16ull * n_tracks))) return rc;
     if ((rc = c->meta.reserve(std::max<uint64_t>(L.meta_total, 1)))) return rc;
-    if ((rc = c->h_small.reserve(sizeof(TrackDev) * n_tracks + L.meta_total + 16ull * n_tracks + 64))) return rc;
+    if ((rc = c->h_small.reserve(sizeof(TrackDev) * n_tracks + L.meta_total + 16ull * n_tracks + 256))) return rc;
 
     const size_t smem_static = align_up(encode_static_smem(), 16);
     const size_t dyn = c->smem_optin;
@@ -358,6 +421,7 @@ static int encode_batch_impl(flo_ctx *c, const flo_track *tracks, size_t n_track
     ep.ticket = (uint32_t *)((uint8_t *)c->ctrl.p + 8ull * NF);
     ep.err = ep.ticket + 1;
     ep.counters = ep.ticket + 2;
+    ep.phase_cycles = (unsigned long long *)(ep.ticket + 16);
     ep.frame_excl = (unsigned long long *)c->fexcl.p;
     ep.frame_size = (uint32_t *)c->fsize.p;
     ep.plane_scratch = (int16_t *)c->plane.p;
@@ -371,7 +435,7 @@ static int encode_batch_impl(flo_ctx *c, const flo_track *tracks, size_t n_track
     fp.tracks = ep.tracks; fp.n_tracks = NTR; fp.n_frames = NF; fp.level = level; fp.frames = ep.frames;
     fp.out = out; fp.meta = (const uint8_t *)c->meta.p;
     fp.frame_excl = ep.frame_excl; fp.frame_size = ep.frame_size;
-    fp.track_crc = ep.ticket + 16; fp.n_segs = NSEG;
+    fp.track_crc = ep.ticket + 32; fp.n_segs = NSEG;
     fp.file_off = (unsigned long long *)c->foff.p;
     fp.file_len = fp.file_off + n_tracks;
 
@@ -395,11 +459,12 @@ static int encode_batch_impl(flo_ctx *c, const flo_track *tracks, size_t n_track
     uint64_t *h_off = (uint64_t *)(hs + align_up(sizeof(TrackDev) * n_tracks + L.meta_total, 16));
     uint32_t *h_err = (uint32_t *)(h_off + 2 * n_tracks);           // err + 8 counters
     CK(cudaMemcpyAsync(h_off, c->foff.p, 16ull * n_tracks, cudaMemcpyDeviceToHost, st));
-    CK(cudaMemcpyAsync(h_err, ep.err, 4 * 9, cudaMemcpyDeviceToHost, st));
+    CK(cudaMemcpyAsync(h_err, ep.err, 4 * 31, cudaMemcpyDeviceToHost, st));   // err, counters[8], pad, phase clocks
     CK(cudaStreamSynchronize(st));
     if (*h_err) { set_err("device-side consistency check failed (code 0x%08x)", *h_err); return FLO_ERR_INTERNAL; }
     for (size_t t = 0; t < n_tracks; t++) { offsets[t] = h_off[t]; lens[t] = h_off[n_tracks + t]; }
     for (int i = 0; i < 8; i++) c->counters[i] = h_err[1 + i];
+    for (int i = 0; i < 8; i++) memcpy(&c->counters[8 + i], &h_err[15 + 2 * i], 8);
 
     float t_all = 0, t_enc = 0, t_toc = 0, t_crc = 0, t_hdr = 0, t_setup = 0, t_h2d = 0;
     cudaEventElapsedTime(&t_h2d, c->ev[0], c->ev[1]);
@@ -433,8 +498,22 @@ extern "C" int flo_encode_batch(flo_ctx *c, const flo_track *tracks, size_t n_tr
     // one D2H of the compact image region, then split per track
     uint64_t total = 0;
     for (size_t t = 0; t < n_tracks; t++) total = std::max(total, off[t] + len[t]);
-    if ((rc = c->h_out.reserve(total + 16))) return rc;
     cudaStream_t st = c->stream;
+    if (total >= SMALL_OUTPUT) {
+        // large result: straight into a pinned block, pointers into it are handed out (flo_free recycles it)
+        OutBlock *blk = take_block(total + 16);
+        if (!blk) { set_err("cudaMallocHost(%llu) failed for the output block", (unsigned long long)total); return FLO_ERR_NOMEM; }
+        cudaError_t e = cudaEventRecord(c->ev[0], st);
+        if (e == cudaSuccess) e = cudaMemcpyAsync(blk->base, c->out.p, total, cudaMemcpyDeviceToHost, st);
+        if (e == cudaSuccess) e = cudaEventRecord(c->ev[1], st);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+        if (e != cudaSuccess) { drop_block(blk); set_err("D2H of the result failed: %s", cudaGetErrorString(e)); return FLO_ERR_CUDA; }
+        cudaEventElapsedTime(&c->ms[5], c->ev[0], c->ev[1]);
+        for (size_t t = 0; t < n_tracks; t++) { outs[t].data = blk->base + off[t]; outs[t].len = (size_t)len[t]; }
+        publish_block(blk, n_tracks);
+        return FLO_OK;
+    }
+    if ((rc = c->h_out.reserve(total + 16))) return rc;
     CK(cudaEventRecord(c->ev[0], st));
     CK(cudaMemcpyAsync(c->h_out.p, c->out.p, total, cudaMemcpyDeviceToHost, st));
     CK(cudaEventRecord(c->ev[1], st));

@@ -67,6 +67,7 @@ struct EncodeParams {
     uint32_t *counters;               // [0] loud frames, [1] pass-3 rounds, [2] LPC sizes from the window, [3] window misses,
                                       // [4] fixed candidates evaluated exactly, [5] candidates pruned by bounds
     uint32_t smem_plane_bytes;        // bytes of dynamic shared memory available for sample planes
+    unsigned long long *phase_cycles; // [0] ingest, [1] analysis, [2] look-back, [3] pack, [4] whole frame (SM clocks, thread 0)
 };
 
 struct FinalParams {

@@ -63,13 +63,17 @@ class Context:
         return d
 
     def last_counters(self) -> dict:
-        buf = (C.c_uint64 * 8)()
+        buf = (C.c_uint64 * 16)()
         _lib.check(self._L.flo_ctx_last_counters(self._h, buf))
         keys = ["loud_frames", "exact_rounds", "lpc_window_hits", "lpc_window_misses", "fixed_exact", "pruned"]
-        return {k: int(v) for k, v in zip(keys, buf)}
+        d = {k: int(v) for k, v in zip(keys, buf)}
+        d["phase_clocks"] = {k: int(buf[8 + i]) for i, k in enumerate(["ingest", "analysis", "lookback", "pack", "frame", "pack_codes", "pack_scan", "pack_emit"])}
+        return d
 
     # -- encode entries ----------------------------------------------------------------
-    def encode_batch(self, tracks: Sequence["TrackSpec"], level: int = 5, fmt: int = FMT_F32) -> List[bytes]:
+    def encode_batch(self, tracks: Sequence["TrackSpec"], level: int = 5, fmt: int = FMT_F32, views: bool = False):
+        """Returns a list of `bytes`; with views=True a BatchResult of zero-copy uint8 arrays over the library's
+        (pinned) output buffers, valid until its close()."""
         n = len(tracks)
         if n == 0:
             return []
@@ -90,6 +94,8 @@ class Context:
             arr[i].meta_len = len(m)
         outs = (_lib.Out * n)()
         _lib.check(self._L.flo_encode_batch(self._h, arr, n, fmt, min(int(level), 255), outs))
+        if views:
+            return BatchResult(self._L, outs)
         res = []
         for o in outs:
             res.append(C.string_at(o.data, o.len) if o.len else b"")
@@ -137,6 +143,43 @@ class Context:
         if b == 0:
             raise FloError(_lib.last_error())
         return b + extra
+
+
+class BatchResult:
+    """Zero-copy views of the file images returned by flo_encode_batch; close() hands them back (flo_free)."""
+
+    def __init__(self, L, outs):
+        self._L, self._outs = L, outs
+        self.arrays = [np.ctypeslib.as_array(C.cast(o.data, C.POINTER(C.c_uint8)), shape=(o.len,)) if o.len
+                       else np.zeros(0, np.uint8) for o in outs]
+
+    def __len__(self):
+        return len(self.arrays)
+
+    def __getitem__(self, i):
+        return self.arrays[i]
+
+    def total_bytes(self) -> int:
+        return int(sum(a.size for a in self.arrays))
+
+    def close(self) -> None:
+        if self._outs is not None:
+            self.arrays = []
+            for o in self._outs:
+                self._L.flo_free(o.data)
+            self._outs = None
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        self.close()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
 
 
 def _u(v: int, bits: int, name: str) -> int:

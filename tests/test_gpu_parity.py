@@ -272,3 +272,21 @@ def test_errors_like_reference_panics(fb):
         fb.Encoder(44100, 0, 16).encode(np.zeros(4, np.float32), b"")
     with pytest.raises(fb.FloError):
         fb.Encoder(0, 1, 16).encode(np.zeros(4, np.float32), b"")
+
+
+def test_zero_copy_views_and_output_pool(fb, ctx):
+    """Large results come back in pooled pinned blocks; views and bytes agree and blocks are reusable."""
+    sr, ch = 44100, 2
+    specs, want = [], []
+    for i in range(3):
+        pcm = synth_pcm16(12 * sr + i, ch, sr, seed=70 + i)
+        x = pcm16_to_f32(pcm)
+        specs.append(fb.TrackSpec(x, sr, ch, 16, b"m%d" % i))
+    plain = ctx.encode_batch(specs, 5)
+    assert sum(len(b) for b in plain) > (1 << 20)
+    for rep in range(3):
+        with ctx.encode_batch(specs, 5, views=True) as res:
+            assert len(res) == 3
+            for a, b in zip(res.arrays, plain):
+                assert a.tobytes() == b
+    check_same(plain[1], oracle.encode(specs[1].samples, sr, ch, 16, 5, b"m1"), "batch track 1")
