@@ -44,6 +44,7 @@ struct Smem {
     i32 wcoef[MAXORD];                // winner's coefficients while packing
     double wqd[MAXORD];
     u32 scan_warp[2][NWARP];
+    u32 cnt[8];                       // analysis counters of this CTA (flushed at kernel end)
     u32 g;                            // current global frame
     i32 ms;                           // mid/side chosen (encoder.rs:94-100)
     i32 loud;
@@ -161,13 +162,16 @@ __device__ void levinson_all_orders(ChanState &cs) {
             const double v = __ddiv_rn(1073741824.0, mx);
             const int e = isinf(v) ? 255 : ilogb(v);
             const int shift = e < 0 ? 0 : (e > 15 ? 15 : e);
-            const double scale = (double)(1ll << shift);
+            const double scale = (double)(1 << shift), inv_scale = 1.0 / scale;    // powers of two: exact
 #pragma unroll
             for (int j = 0; j <= i; j++) {
-                const double q = round(__dmul_rn(a[j], scale));       // f64::round: half away from zero
+                // f64::round (half away from zero): trunc, then one more if the (exact) remainder reaches 1/2
+                const double y = __dmul_rn(a[j], scale);
+                double q = trunc(y);
+                if (fabs(y - q) >= 0.5) q += copysign(1.0, y);
                 const i32 qi = q >= 2147483647.0 ? 2147483647 : (q <= -2147483648.0 ? (-2147483647 - 1) : (i32)q);
                 cs.qc[o - 5][j] = qi;
-                cs.qd[o - 5][j] = ldexp((double)qi, -shift);
+                cs.qd[o - 5][j] = (double)qi * inv_scale;
             }
             cs.lpc_shift[o - 5] = shift;
             cs.lpc_ok[o - 5] = 1;
@@ -587,6 +591,7 @@ __device__ void after_pass1(ChanState &cs, int fmax, bool lpc_on) {
 
 // after pass 2: resolve the LPC candidates (encoder.rs:262-286)
 __device__ void after_pass2(ChanState &cs, int P, u32 *counters) {
+    u32 hits = 0, misses = 0;
     const u32 n = (u32)cs.n;
     for (int o = 5; o <= P; o++) {
         const int i = o - 5, c = 1 + o;
@@ -602,12 +607,14 @@ __device__ void after_pass2(ChanState &cs, int P, u32 *counters) {
             const u64 S = jj == cs.lpc_j0[i] ? cs.l_t0[i] : cs.l_t1[i];
             cs.cand_state[c] = CS_EXACT;
             cs.cand_size[c] = rice_bytes(S, cs.l_sum[i], n, k);
-            atomicAdd(counters + 2, 1u);
+            hits++;
         } else {
             cs.cand_state[c] = CS_BOUNDED;
-            atomicAdd(counters + 3, 1u);                            // window miss or 2^19 <= max|r| < 2^20
+            misses++;                            // window miss or 2^19 <= max|r| < 2^20
         }
     }
+    if (hits) atomicAdd(counters + 2, hits);
+    if (misses) atomicAdd(counters + 3, misses);
 }
 
 // Pick the next candidate that still needs an exact evaluation: bounded, and its lower bound
@@ -628,13 +635,15 @@ __device__ int next_open_candidate(ChanState &cs, bool prune, u32 *counters) {
     }
     int pick = -1;
     i64 pick_lb = INT64_MAX;
+    u32 pruned = 0;
     for (int j = 0; j < NCAND; j++) {
         if (cs.cand_state[j] != CS_BOUNDED) continue;
         i64 lb, ub;
         rice_bounds(cs.cand_sumabs[j], n, cs.cand_k[j], lb, ub);
-        if (prune && lb > best_ub) { cs.cand_state[j] = CS_ABSENT; atomicAdd(counters + 5, 1u); continue; }   // provably not the winner
+        if (prune && lb > best_ub) { cs.cand_state[j] = CS_ABSENT; pruned++; continue; }   // provably not the winner
         if (lb < pick_lb) { pick_lb = lb; pick = j; }
     }
+    if (pruned) atomicAdd(counters + 5, pruned);
     if (pick >= 1 && pick <= 5) atomicAdd(counters + 4, 1u);
     return pick;
 }
@@ -1071,6 +1080,7 @@ __global__ void __launch_bounds__(NT, 1) k_encode_frames(const EncodeParams p) {
     int16_t *smem_planes = reinterpret_cast<int16_t *>(dyn_smem + ((sizeof(Smem) + 15) & ~size_t(15)));
     const int tid = threadIdx.x;
     for (int i = tid; i < RING_WORDS; i += NT) s.ring[i] = 0;
+    if (tid < 8) s.cnt[tid] = 0;
     ChanResult *cres = p.cres + (size_t)blockIdx.x * 256;
     const int level = p.level;
     // P = LPC max order analysed by this instantiation (0: levels 0-3, fixed predictors only)
@@ -1082,6 +1092,10 @@ __global__ void __launch_bounds__(NT, 1) k_encode_frames(const EncodeParams p) {
     for (;;) {
         __syncthreads();
         if (tid == 0) {
+            // A ticket is taken only when the CTA is ready to start the frame: frames are then published
+            // (look-back status) in nearly ticket order.  Taking tickets one frame ahead (to prefetch the next
+            // frame's samples into L2) was tried: a CTA that lags then holds an early ticket for a whole frame
+            // time and every later frame stalls in the look-back -- 1.4 ms -> 2.0 ms per 1184 frames.
             s.g = atomicAdd(p.ticket, 1u);
             s.loud = 0; s.ms = 0;
             s.ms_var[0] = s.ms_var[1] = s.ms_var[2] = 0;
@@ -1133,7 +1147,7 @@ __global__ void __launch_bounds__(NT, 1) k_encode_frames(const EncodeParams p) {
         }
 
         const long long tc1 = clock64();
-        if (tid == 0) atomicAdd(p.counters, 1u);
+        if (tid == 0) atomicAdd(&s.cnt[0], 1u);
         // mid/side decision, encoder.rs:94-100, 131-153
         int ms = 0;
         if (C == 2) {
@@ -1165,13 +1179,16 @@ __global__ void __launch_bounds__(NT, 1) k_encode_frames(const EncodeParams p) {
                 cs.ex_cand = -1; cs.ex_s = 0; cs.ex_max = 0;
             }
             __syncthreads();
+            const long long ta0 = clock64();
             bool any_lpc = false;
             for (int q = 0; q < nch; q++) any_lpc |= lpc_on && s.cs[q].n > 5;
             if (any_lpc) pass1<P>(s, nch);
             else pass1<0>(s, nch);
             __syncthreads();
+            const long long ta1 = clock64();
             if (tid < nch && s.cs[tid].n > 0) after_pass1<P>(s.cs[tid], fmax, lpc_on);
             __syncthreads();
+            const long long ta2 = clock64();
             bool run2 = false;
             for (int q = 0; q < nch; q++)
                 for (int o = 0; o < NLPC; o++) run2 |= s.cs[q].n > 0 && s.cs[q].lpc_ok[o] != 0;
@@ -1179,10 +1196,11 @@ __global__ void __launch_bounds__(NT, 1) k_encode_frames(const EncodeParams p) {
                 if constexpr (P > 0) pass2<P>(s, nch);
                 __syncthreads();
             }
+            const long long ta3 = clock64();
             if (tid < nch && s.cs[tid].n > 0) {
                 ChanState &cs = s.cs[tid];
-                if (run2) after_pass2(cs, P, p.counters);
-                cs.ex_cand = next_open_candidate(cs, prune, p.counters);
+                if (run2) after_pass2(cs, P, s.cnt);
+                cs.ex_cand = next_open_candidate(cs, prune, s.cnt);
                 cs.ex_s = 0; cs.ex_max = 0;
             }
             __syncthreads();
@@ -1191,16 +1209,21 @@ __global__ void __launch_bounds__(NT, 1) k_encode_frames(const EncodeParams p) {
                 bool more = false;
                 for (int q = 0; q < nch; q++) more |= s.cs[q].n > 0 && s.cs[q].ex_cand >= 0;
                 if (!more) break;
-                if (tid == 0) atomicAdd(p.counters + 1, 1u);
+                if (tid == 0) atomicAdd(&s.cnt[1], 1u);
                 pass3<P>(s, nch);
                 __syncthreads();
                 if (tid < nch && s.cs[tid].n > 0) {
                     ChanState &cs = s.cs[tid];
                     after_pass3(cs);
-                    cs.ex_cand = next_open_candidate(cs, prune, p.counters);
+                    cs.ex_cand = next_open_candidate(cs, prune, s.cnt);
                     cs.ex_s = 0; cs.ex_max = 0;
                 }
                 __syncthreads();
+            }
+            if (tid == 0) {
+                const long long ta4 = clock64();
+                atomicAdd(p.phase_cycles + 8, (u64)(ta1 - ta0)); atomicAdd(p.phase_cycles + 9, (u64)(ta2 - ta1));
+                atomicAdd(p.phase_cycles + 10, (u64)(ta3 - ta2)); atomicAdd(p.phase_cycles + 11, (u64)(ta4 - ta3));
             }
             // encode_channel_int, encoder.rs:184-216: strictly smaller wins, candidates in order
             if (tid < nch) {
@@ -1303,4 +1326,6 @@ __global__ void __launch_bounds__(NT, 1) k_encode_frames(const EncodeParams p) {
             atomicAdd(p.phase_cycles + 4, (u64)(tc4 - tc0));
         }
     }
+    __syncthreads();
+    if (tid < 8 && s.cnt[tid]) atomicAdd(p.counters + tid, s.cnt[tid]);
 }

@@ -163,7 +163,7 @@ struct flo_ctx {
     cudaStream_t own_stream = nullptr, stream = nullptr;
     cudaEvent_t ev[8] = {};
     DevBuf in, out, meta, tracks, frames, ctrl, fexcl, fsize, foff, plane, cres, report;
-    uint64_t counters[16] = {0};      // [0..7] analysis counters, [8..15] per-phase SM clock sums
+    uint64_t counters[24] = {0};      // [0..7] analysis counters, [8..23] per-phase SM clock sums
     HostBuf h_small, h_out;
     bool report_on = false;
     uint32_t report_frames = 0;
@@ -233,7 +233,7 @@ extern "C" int flo_ctx_last_timing(flo_ctx *c, float ms[6], uint32_t *launches) 
     return FLO_OK;
 }
 
-extern "C" int flo_ctx_last_counters(flo_ctx *c, uint64_t out[16]) {
+extern "C" int flo_ctx_last_counters(flo_ctx *c, uint64_t out[24]) {
     if (!c || !out) { set_err("bad argument"); return FLO_ERR_ARG; }
     std::lock_guard<std::mutex> lk(c->mu);
     memcpy(out, c->counters, sizeof c->counters);
@@ -358,7 +358,7 @@ static int encode_batch_impl(flo_ctx *c, const flo_track *tracks, size_t n_track
     const uint32_t NF = (uint32_t)L.n_frames, NSEG = (uint32_t)L.n_segs, NTR = (uint32_t)n_tracks;
     if ((rc = c->tracks.reserve(sizeof(TrackDev) * n_tracks))) return rc;
     if ((rc = c->frames.reserve(sizeof(uint2) * std::max<uint64_t>(NF, 1)))) return rc;
-    const size_t ctrl_bytes = 8ull * NF + 128 + 4ull * n_tracks;       // status words, ticket, err, counters, phase clocks, track CRCs
+    const size_t ctrl_bytes = 8ull * NF + 256 + 4ull * n_tracks;       // status words, ticket, err, counters, phase clocks, track CRCs
     if ((rc = c->ctrl.reserve(ctrl_bytes))) return rc;
     if ((rc = c->fexcl.reserve(8ull * std::max<uint64_t>(NF, 1)))) return rc;
     if ((rc = c->fsize.reserve(4ull * std::max<uint64_t>(NF, 1)))) return rc;
@@ -435,7 +435,7 @@ static int encode_batch_impl(flo_ctx *c, const flo_track *tracks, size_t n_track
     fp.tracks = ep.tracks; fp.n_tracks = NTR; fp.n_frames = NF; fp.level = level; fp.frames = ep.frames;
     fp.out = out; fp.meta = (const uint8_t *)c->meta.p;
     fp.frame_excl = ep.frame_excl; fp.frame_size = ep.frame_size;
-    fp.track_crc = ep.ticket + 32; fp.n_segs = NSEG;
+    fp.track_crc = ep.ticket + 48; fp.n_segs = NSEG;
     fp.file_off = (unsigned long long *)c->foff.p;
     fp.file_len = fp.file_off + n_tracks;
 
@@ -459,12 +459,12 @@ static int encode_batch_impl(flo_ctx *c, const flo_track *tracks, size_t n_track
     uint64_t *h_off = (uint64_t *)(hs + align_up(sizeof(TrackDev) * n_tracks + L.meta_total, 16));
     uint32_t *h_err = (uint32_t *)(h_off + 2 * n_tracks);           // err + 8 counters
     CK(cudaMemcpyAsync(h_off, c->foff.p, 16ull * n_tracks, cudaMemcpyDeviceToHost, st));
-    CK(cudaMemcpyAsync(h_err, ep.err, 4 * 31, cudaMemcpyDeviceToHost, st));   // err, counters[8], pad, phase clocks
+    CK(cudaMemcpyAsync(h_err, ep.err, 4 * 47, cudaMemcpyDeviceToHost, st));   // err, counters[8], pad, phase clocks[16]
     CK(cudaStreamSynchronize(st));
     if (*h_err) { set_err("device-side consistency check failed (code 0x%08x)", *h_err); return FLO_ERR_INTERNAL; }
     for (size_t t = 0; t < n_tracks; t++) { offsets[t] = h_off[t]; lens[t] = h_off[n_tracks + t]; }
     for (int i = 0; i < 8; i++) c->counters[i] = h_err[1 + i];
-    for (int i = 0; i < 8; i++) memcpy(&c->counters[8 + i], &h_err[15 + 2 * i], 8);
+    for (int i = 0; i < 16; i++) memcpy(&c->counters[8 + i], &h_err[15 + 2 * i], 8);
 
     float t_all = 0, t_enc = 0, t_toc = 0, t_crc = 0, t_hdr = 0, t_setup = 0, t_h2d = 0;
     cudaEventElapsedTime(&t_h2d, c->ev[0], c->ev[1]);

@@ -63,11 +63,12 @@ class Context:
         return d
 
     def last_counters(self) -> dict:
-        buf = (C.c_uint64 * 16)()
+        buf = (C.c_uint64 * 24)()
         _lib.check(self._L.flo_ctx_last_counters(self._h, buf))
         keys = ["loud_frames", "exact_rounds", "lpc_window_hits", "lpc_window_misses", "fixed_exact", "pruned"]
         d = {k: int(v) for k, v in zip(keys, buf)}
-        d["phase_clocks"] = {k: int(buf[8 + i]) for i, k in enumerate(["ingest", "analysis", "lookback", "pack", "frame", "pack_codes", "pack_scan", "pack_emit"])}
+        d["phase_clocks"] = {k: int(buf[8 + i]) for i, k in enumerate(["ingest", "analysis", "lookback", "pack", "frame", "pack_codes", "pack_scan", "pack_emit",
+                                                                 "pass1", "levinson", "pass2", "exact_select"])}
         return d
 
     # -- encode entries ----------------------------------------------------------------

@@ -112,8 +112,9 @@ int flo_ctx_last_timing(flo_ctx *ctx, float ms[6], uint32_t *launches);
 /* Analysis counters of the last batch call (diagnostics): [0] non-silent frames, [1] exact-size
  * re-evaluation rounds, [2] LPC candidates sized in the single pass, [3] LPC candidates that needed the
  * exact pass, [4] fixed candidates evaluated exactly, [5] candidates excluded by size bounds;
- * [8..12] SM clocks summed over frames in ingest, analysis, look-back, pack, whole frame. */
-int flo_ctx_last_counters(flo_ctx *ctx, uint64_t out[16]);
+ * [8..23] SM clocks (thread 0) summed over frames: ingest, analysis, look-back, pack, whole frame,
+ * pack codes / scan / emit, pass 1, Levinson, pass 2, exact rounds + selection. */
+int flo_ctx_last_counters(flo_ctx *ctx, uint64_t out[24]);
 
 /* Per-frame analysis report of the last batch call, for parity tests: for
  * global frame g and channel c (< 8), candidate j (raw, fixed 0..4, lpc
