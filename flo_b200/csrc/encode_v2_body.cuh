@@ -24,6 +24,7 @@ struct ChanState {
     i32 lpc_ok[NLPC];
     i32 lpc_shift[NLPC];
     i32 lpc_j0[NLPC];                 // guessed shift window {j0, j0 + 1} for sum(w >> j)
+    double lpc_err[NLPC];             // prediction error after each order (window guess only)
     // pass 2: LPC statistics
     u64 l_sum[NLPC];
     u32 l_or[NLPC];
@@ -91,7 +92,7 @@ __device__ __forceinline__ int rice_k_or(u32 or_abs, u64 sum_abs, u32 n) {
     if (or_abs == 0) return 0;
     const int bl = bitlen32(or_abs);              // bitlen(max_abs)
     const int min_k = bl >= 8 ? bl + 1 - 8 : 0;   // 2 max > 255  <=>  max >= 128; bits_needed = bl + 1
-    const u32 mean = (u32)(sum_abs / (u64)n);
+    const u32 mean = (sum_abs >> 32) == 0 ? (u32)sum_abs / n : (u32)(sum_abs / (u64)n);
     const int mean_k = mean > 0 ? bitlen32(mean) : 0;
     const int k = max(min_k, mean_k);
     return min(k, 15);
@@ -126,69 +127,90 @@ __device__ __forceinline__ void rice_bounds(u64 sum_abs, u32 n, int k, i64 &lb, 
 // iteration m-1), so one run to order P yields every order 5..P.  Also derives, per order,
 // the guessed shift window for the single-pass size evaluation from the prediction error.
 template <int P>
-__device__ void levinson_all_orders(ChanState &cs) {
-    for (int o = 0; o < NLPC; o++) { cs.lpc_ok[o] = 0; cs.lpc_shift[o] = 0; cs.lpc_j0[o] = 0; }
-    if (cs.ac[0] == 0) return;
-    double a[P > 0 ? P : 1], nc[P > 0 ? P : 1], acd[P + 1];
+__device__ void levinson_all_orders(ChanState &cs) {      // called by a full warp
+    const int lane = threadIdx.x & 31;
+    if (lane < NLPC) { cs.lpc_ok[lane] = 0; cs.lpc_shift[lane] = 0; cs.lpc_j0[lane] = 0; }
+    __syncwarp();
+    // (1) the recursion itself is sequential: lane 0.  Unquantised coefficients of every order >= 5 are
+    //     parked in cs.qd (overwritten by their quantised form below), the prediction error in cs.lpc_err.
+    if (lane == 0 && cs.ac[0] != 0) {
+        double a[P > 0 ? P : 1], nc[P > 0 ? P : 1], acd[P + 1];
 #pragma unroll
-    for (int i = 0; i < P; i++) a[i] = 0.0;
+        for (int i = 0; i < P; i++) a[i] = 0.0;
 #pragma unroll
-    for (int i = 0; i <= P; i++) acd[i] = (double)cs.ac[i];
-    double err = acd[0];
-    bool alive = true;
+        for (int i = 0; i <= P; i++) acd[i] = (double)cs.ac[i];
+        double err = acd[0];
+        bool alive = true;
 #pragma unroll
-    for (int i = 0; i < P; i++) {
-        if (!alive) break;
-        double lambda = acd[i + 1];
+        for (int i = 0; i < P; i++) {
+            if (!alive) break;
+            double lambda = acd[i + 1];
 #pragma unroll
-        for (int j = 0; j < i; j++) lambda = __dsub_rn(lambda, __dmul_rn(a[j], acd[i - j]));
-        if (fabs(err) < 1e-10) { alive = false; break; }
-        const double gamma = __ddiv_rn(lambda, err);
-        if (fabs(gamma) >= 1.0) { alive = false; break; }
-        nc[i] = gamma;
+            for (int j = 0; j < i; j++) lambda = __dsub_rn(lambda, __dmul_rn(a[j], acd[i - j]));
+            if (fabs(err) < 1e-10) { alive = false; break; }
+            const double gamma = __ddiv_rn(lambda, err);
+            if (fabs(gamma) >= 1.0) { alive = false; break; }
+            nc[i] = gamma;
 #pragma unroll
-        for (int j = 0; j < i; j++) nc[j] = __dsub_rn(a[j], __dmul_rn(gamma, a[i - 1 - j]));
+            for (int j = 0; j < i; j++) nc[j] = __dsub_rn(a[j], __dmul_rn(gamma, a[i - 1 - j]));
 #pragma unroll
-        for (int j = 0; j <= i; j++) a[j] = nc[j];
-        err = __dmul_rn(err, __dsub_rn(1.0, __dmul_rn(gamma, gamma)));
-        const int o = i + 1;
-        if (o >= 5) {
-            double mx = 0.0;
+            for (int j = 0; j <= i; j++) a[j] = nc[j];
+            err = __dmul_rn(err, __dsub_rn(1.0, __dmul_rn(gamma, gamma)));
+            if (i + 1 >= 5) {
 #pragma unroll
-            for (int j = 0; j <= i; j++) { double t = fabs(a[j]); if (t == t && t > mx) mx = t; }
-            if (mx == 0.0 || isinf(mx)) continue;
+                for (int j = 0; j <= i; j++) cs.qd[i + 1 - 5][j] = a[j];
+                cs.lpc_err[i + 1 - 5] = err;
+                cs.lpc_ok[i + 1 - 5] = 2;                  // reached; validated in (2)
+            }
+        }
+    }
+    __syncwarp();
+    // (2) per order (lane t = order - 5): max |a|, shift, and the size-window guess
+    if (lane < P - 4 && cs.lpc_ok[lane] == 2) {
+        const int o = 5 + lane;
+        double mx = 0.0;
+        for (int j = 0; j < o; j++) { const double t = fabs(cs.qd[lane][j]); if (t == t && t > mx) mx = t; }
+        int ok = 0;
+        if (!(mx == 0.0 || isinf(mx))) {
             // shift = min(floor(log2(2^30 / max)) as u8, 15); floor(log2(v)) of a positive finite
             // double is its binary exponent (|a_j| <= C(12,6) = 924 makes this 15 in practice).
             const double v = __ddiv_rn(1073741824.0, mx);
             const int e = isinf(v) ? 255 : ilogb(v);
-            const int shift = e < 0 ? 0 : (e > 15 ? 15 : e);
-            const double scale = (double)(1 << shift), inv_scale = 1.0 / scale;    // powers of two: exact
-#pragma unroll
-            for (int j = 0; j <= i; j++) {
-                // f64::round (half away from zero): trunc, then one more if the (exact) remainder reaches 1/2
-                const double y = __dmul_rn(a[j], scale);
-                double q = trunc(y);
-                if (fabs(y - q) >= 0.5) q += copysign(1.0, y);
-                const i32 qi = q >= 2147483647.0 ? 2147483647 : (q <= -2147483648.0 ? (-2147483647 - 1) : (i32)q);
-                cs.qc[o - 5][j] = qi;
-                cs.qd[o - 5][j] = (double)qi * inv_scale;
-            }
-            cs.lpc_shift[o - 5] = shift;
-            cs.lpc_ok[o - 5] = 1;
+            cs.lpc_shift[lane] = e < 0 ? 0 : (e > 15 ? 15 : e);
+            ok = 1;
             // Heuristic only (exactness never depends on it): mean|r| ~ 0.64 * rms(r), rms^2 ~ err / n.
             // The window {j0, j0+1} must contain max(k-1, 0); a miss is re-evaluated exactly in pass 3.
             // log2 via the exponent and a linear mantissa term is accurate to 0.09, ample here.
+            const double err = cs.lpc_err[lane];
             const double rms2 = err > 0.0 ? err / (double)cs.n : 0.0;
             double lg = -10.0;
             if (rms2 > 1e-30) {
                 int ex;
-                const double m = frexp(rms2, &ex);                    // rms2 = m 2^ex, m in [0.5, 1)
+                const double m = frexp(rms2, &ex);        // rms2 = m 2^ex, m in [0.5, 1)
                 lg = 0.5 * ((double)ex + 2.0 * m - 2.0) - 0.64;
             }
             const int j0 = (int)floor(lg - 0.5);
-            cs.lpc_j0[o - 5] = j0 < 0 ? 0 : (j0 > 14 ? 14 : j0);
+            cs.lpc_j0[lane] = j0 < 0 ? 0 : (j0 > 14 ? 14 : j0);
+        }
+        cs.lpc_ok[lane] = ok;
+    }
+    __syncwarp();
+    // (3) quantise every (order, j) pair in parallel (lpc.rs:263-273)
+    for (int item = lane; item < (P - 4) * P; item += 32) {
+        const int t = item / (P > 0 ? P : 1), j = item % (P > 0 ? P : 1);
+        if (j < 5 + t && cs.lpc_ok[t] == 1) {
+            const int shift = cs.lpc_shift[t];
+            const double scale = (double)(1 << shift), inv_scale = 1.0 / scale;      // powers of two: exact
+            // f64::round (half away from zero): trunc, then one more if the (exact) remainder reaches 1/2
+            const double y = __dmul_rn(cs.qd[t][j], scale);
+            double q = trunc(y);
+            if (fabs(y - q) >= 0.5) q += copysign(1.0, y);
+            const i32 qi = q >= 2147483647.0 ? 2147483647 : (q <= -2147483648.0 ? (-2147483647 - 1) : (i32)q);
+            cs.qc[t][j] = qi;
+            cs.qd[t][j] = (double)qi * inv_scale;
         }
     }
+    __syncwarp();
 }
 
 // ----------------------------------------------------------------------------
@@ -569,82 +591,108 @@ __device__ void pass3(Smem &s, int nch) {
 // ----------------------------------------------------------------------------
 // candidate bookkeeping (one thread per channel)
 // ----------------------------------------------------------------------------
+// The candidate bookkeeping below runs on one full warp per channel: lane j owns candidate j
+// (0 raw, 1..5 fixed 0..4, 6..13 LPC 5..12); lane 0 additionally runs the Levinson recursion.
+
 // after pass 1: k of every fixed candidate, raw size; then Levinson
 template <int P>
-__device__ void after_pass1(ChanState &cs, int fmax, bool lpc_on) {
+__device__ void after_pass1_warp(ChanState &cs, int fmax, bool lpc_on) {
+    const int lane = threadIdx.x & 31;
     const u32 n = (u32)cs.n;
-    for (int j = 0; j < NCAND; j++) { cs.cand_state[j] = CS_ABSENT; cs.cand_k[j] = 0; cs.cand_size[j] = -1; cs.cand_sumabs[j] = 0; }
-    cs.cand_state[0] = CS_EXACT;
-    cs.cand_size[0] = 2ll * n;                                         // encode_raw, encoder.rs:220-226
-    for (int o = 0; o <= fmax; o++) {
-        cs.cand_state[1 + o] = CS_BOUNDED;
-        cs.cand_k[1 + o] = rice_k_or(cs.fix_or[o], cs.fix_sum[o], n);
-        cs.cand_sumabs[1 + o] = cs.fix_sum[o];
+    if (lane < NCAND) {
+        int state = CS_ABSENT, k = 0;
+        i64 size = -1;
+        u64 sumabs = 0;
+        if (lane == 0) { state = CS_EXACT; size = 2ll * n; }                       // encode_raw, encoder.rs:220-226
+        if (lane >= 1 && lane <= 1 + fmax) {
+            const int o = lane - 1;
+            state = CS_BOUNDED;
+            k = rice_k_or(cs.fix_or[o], cs.fix_sum[o], n);
+            sumabs = cs.fix_sum[o];
+        }
+        cs.cand_state[lane] = state; cs.cand_k[lane] = k; cs.cand_size[lane] = size; cs.cand_sumabs[lane] = sumabs;
     }
-    for (int o = 0; o < NLPC; o++) cs.lpc_ok[o] = 0;
+    if (lane < NLPC) cs.lpc_ok[lane] = 0;
+    __syncwarp();
     if (lpc_on && cs.n > 5) {
         if constexpr (P > 0) levinson_all_orders<P>(cs);
-        for (int o = 5; o <= P; o++)
-            if (cs.n <= o) cs.lpc_ok[o - 5] = 0;                      // encoder.rs:255-257
+        if (lane < NLPC && cs.n <= 5 + lane) cs.lpc_ok[lane] = 0;                 // encoder.rs:255-257
     }
+    __syncwarp();
 }
 
-// after pass 2: resolve the LPC candidates (encoder.rs:262-286)
-__device__ void after_pass2(ChanState &cs, int P, u32 *counters) {
-    u32 hits = 0, misses = 0;
+// after pass 2 (lanes 6..13): resolve the LPC candidates (encoder.rs:262-286)
+__device__ void after_pass2_warp(ChanState &cs, int P, u32 *counters) {
+    const int lane = threadIdx.x & 31;
     const u32 n = (u32)cs.n;
-    for (int o = 5; o <= P; o++) {
-        const int i = o - 5, c = 1 + o;
-        if (!cs.lpc_ok[i]) continue;
+    bool hit = false, miss = false;
+    const int o = lane - 1;
+    if (lane >= 6 && o <= P && cs.lpc_ok[o - 5]) {
+        const int i = o - 5;
         const u32 orr = cs.l_or[i];
         const int bl = bitlen32(orr);
-        if (bl >= 21) continue;                                       // max|r| >= 2^20 > 1_000_000: rejected
-        const int k = rice_k_or(orr, cs.l_sum[i], n);
-        cs.cand_k[c] = k;
-        cs.cand_sumabs[c] = cs.l_sum[i];
-        const int jj = k >= 1 ? k - 1 : 0;
-        if (bl <= 19 && (jj == cs.lpc_j0[i] || jj == cs.lpc_j0[i] + 1)) {
-            const u64 S = jj == cs.lpc_j0[i] ? cs.l_t0[i] : cs.l_t1[i];
-            cs.cand_state[c] = CS_EXACT;
-            cs.cand_size[c] = rice_bytes(S, cs.l_sum[i], n, k);
-            hits++;
-        } else {
-            cs.cand_state[c] = CS_BOUNDED;
-            misses++;                            // window miss or 2^19 <= max|r| < 2^20
+        if (bl < 21) {                                                            // else max|r| >= 2^20 > 1_000_000: rejected
+            const int k = rice_k_or(orr, cs.l_sum[i], n);
+            cs.cand_k[lane] = k;
+            cs.cand_sumabs[lane] = cs.l_sum[i];
+            const int jj = k >= 1 ? k - 1 : 0;
+            if (bl <= 19 && (jj == cs.lpc_j0[i] || jj == cs.lpc_j0[i] + 1)) {
+                const u64 S = jj == cs.lpc_j0[i] ? cs.l_t0[i] : cs.l_t1[i];
+                cs.cand_state[lane] = CS_EXACT;
+                cs.cand_size[lane] = rice_bytes(S, cs.l_sum[i], n, k);
+                hit = true;
+            } else {
+                cs.cand_state[lane] = CS_BOUNDED;                                 // window miss or 2^19 <= max|r| < 2^20
+                miss = true;
+            }
         }
     }
-    if (hits) atomicAdd(counters + 2, hits);
-    if (misses) atomicAdd(counters + 3, misses);
+    const u32 hm = __ballot_sync(0xffffffffu, hit), mm = __ballot_sync(0xffffffffu, miss);
+    if (lane == 0) {
+        if (hm) atomicAdd(counters + 2, (u32)__popc(hm));
+        if (mm) atomicAdd(counters + 3, (u32)__popc(mm));
+    }
+    __syncwarp();
+}
+
+__device__ __forceinline__ u64 warp_min64(u64 v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) { const u64 t = __shfl_xor_sync(0xffffffffu, v, o); v = t < v ? t : v; }
+    return v;
 }
 
 // Pick the next candidate that still needs an exact evaluation: bounded, and its lower bound
 // does not exceed the best upper bound (otherwise it can never be the strictly-smallest one).
 // Among those the one with the smallest lower bound goes first (it tightens the bound most).
-__device__ int next_open_candidate(ChanState &cs, bool prune, u32 *counters) {
+__device__ int next_open_candidate_warp(ChanState &cs, bool prune, u32 *counters) {
+    const int lane = threadIdx.x & 31;
     const u32 n = (u32)cs.n;
-    i64 best_ub = INT64_MAX;
-    for (int j = 0; j < NCAND; j++) {
-        if (cs.cand_state[j] == CS_EXACT) best_ub = min(best_ub, cs.cand_size[j]);
-        else if (cs.cand_state[j] == CS_BOUNDED) {
-            i64 lb, ub;
-            rice_bounds(cs.cand_sumabs[j], n, cs.cand_k[j], lb, ub);
+    int state = CS_ABSENT;
+    i64 lb = 0, ub = 0;
+    u64 ub_eff = ~0ull;
+    if (lane < NCAND) {
+        state = cs.cand_state[lane];
+        if (state == CS_EXACT) ub_eff = (u64)cs.cand_size[lane];
+        else if (state == CS_BOUNDED) {
+            rice_bounds(cs.cand_sumabs[lane], n, cs.cand_k[lane], lb, ub);
             // an LPC candidate with 2^19 <= max|r| < 2^20 may still be rejected: its upper bound does not count
-            const bool maybe_rejected = j >= 6 && bitlen32(cs.l_or[j - 6]) == 20;
-            if (!maybe_rejected) best_ub = min(best_ub, ub);
+            const bool maybe_rejected = lane >= 6 && bitlen32(cs.l_or[lane - 6]) == 20;
+            if (!maybe_rejected) ub_eff = (u64)ub;
         }
     }
-    int pick = -1;
-    i64 pick_lb = INT64_MAX;
-    u32 pruned = 0;
-    for (int j = 0; j < NCAND; j++) {
-        if (cs.cand_state[j] != CS_BOUNDED) continue;
-        i64 lb, ub;
-        rice_bounds(cs.cand_sumabs[j], n, cs.cand_k[j], lb, ub);
-        if (prune && lb > best_ub) { cs.cand_state[j] = CS_ABSENT; pruned++; continue; }   // provably not the winner
-        if (lb < pick_lb) { pick_lb = lb; pick = j; }
+    const u64 best_ub = warp_min64(ub_eff);
+    const bool dead = state == CS_BOUNDED && prune && (u64)lb > best_ub;          // provably not the winner
+    if (dead) { cs.cand_state[lane] = CS_ABSENT; state = CS_ABSENT; }
+    const u64 key = state == CS_BOUNDED ? (((u64)lb << 8) | (u64)lane) : ~0ull;   // smallest lb, then lowest index
+    const u64 best = warp_min64(key);
+    const int pick = best == ~0ull ? -1 : (int)(best & 0xff);
+    const u32 dm = __ballot_sync(0xffffffffu, dead);
+    if (lane == 0) {
+        if (dm) atomicAdd(counters + 5, (u32)__popc(dm));
+        if (pick >= 1 && pick <= 5) atomicAdd(counters + 4, 1u);
+        cs.ex_cand = pick; cs.ex_s = 0; cs.ex_max = 0;
     }
-    if (pruned) atomicAdd(counters + 5, pruned);
-    if (pick >= 1 && pick <= 5) atomicAdd(counters + 4, 1u);
+    __syncwarp();
     return pick;
 }
 
@@ -1186,7 +1234,7 @@ __global__ void __launch_bounds__(NT, 1) k_encode_frames(const EncodeParams p) {
             else pass1<0>(s, nch);
             __syncthreads();
             const long long ta1 = clock64();
-            if (tid < nch && s.cs[tid].n > 0) after_pass1<P>(s.cs[tid], fmax, lpc_on);
+            if ((tid >> 5) < nch && s.cs[tid >> 5].n > 0) after_pass1_warp<P>(s.cs[tid >> 5], fmax, lpc_on);
             __syncthreads();
             const long long ta2 = clock64();
             bool run2 = false;
@@ -1197,11 +1245,10 @@ __global__ void __launch_bounds__(NT, 1) k_encode_frames(const EncodeParams p) {
                 __syncthreads();
             }
             const long long ta3 = clock64();
-            if (tid < nch && s.cs[tid].n > 0) {
-                ChanState &cs = s.cs[tid];
-                if (run2) after_pass2(cs, P, s.cnt);
-                cs.ex_cand = next_open_candidate(cs, prune, s.cnt);
-                cs.ex_s = 0; cs.ex_max = 0;
+            if ((tid >> 5) < nch && s.cs[tid >> 5].n > 0) {
+                ChanState &cs = s.cs[tid >> 5];
+                if (run2) after_pass2_warp(cs, P, s.cnt);
+                next_open_candidate_warp(cs, prune, s.cnt);
             }
             __syncthreads();
             // exact evaluation of whatever is still open (bounded candidates that can still win)
@@ -1212,11 +1259,11 @@ __global__ void __launch_bounds__(NT, 1) k_encode_frames(const EncodeParams p) {
                 if (tid == 0) atomicAdd(&s.cnt[1], 1u);
                 pass3<P>(s, nch);
                 __syncthreads();
-                if (tid < nch && s.cs[tid].n > 0) {
-                    ChanState &cs = s.cs[tid];
-                    after_pass3(cs);
-                    cs.ex_cand = next_open_candidate(cs, prune, s.cnt);
-                    cs.ex_s = 0; cs.ex_max = 0;
+                if ((tid >> 5) < nch && s.cs[tid >> 5].n > 0) {
+                    ChanState &cs = s.cs[tid >> 5];
+                    if ((tid & 31) == 0) after_pass3(cs);
+                    __syncwarp();
+                    next_open_candidate_warp(cs, prune, s.cnt);
                 }
                 __syncthreads();
             }
