@@ -1122,8 +1122,11 @@ __device__ void ingest_frame(Smem &s, const T *in, u32 len, u32 C, int16_t *plan
 // ----------------------------------------------------------------------------
 extern __shared__ __align__(16) unsigned char dyn_smem[];
 
+#ifndef FLO_MIN_CTAS
+#define FLO_MIN_CTAS 1
+#endif
 template <int P>
-__global__ void __launch_bounds__(NT, 1) k_encode_frames(const EncodeParams p) {
+__global__ void __launch_bounds__(NT, FLO_MIN_CTAS) k_encode_frames(const EncodeParams p) {
     Smem &s = *reinterpret_cast<Smem *>(dyn_smem);
     int16_t *smem_planes = reinterpret_cast<int16_t *>(dyn_smem + ((sizeof(Smem) + 15) & ~size_t(15)));
     const int tid = threadIdx.x;

@@ -367,9 +367,18 @@ static int encode_batch_impl(flo_ctx *c, const flo_track *tracks, size_t n_track
     if ((rc = c->h_small.reserve(sizeof(TrackDev) * n_tracks + L.meta_total + 16ull * n_tracks + 256))) return rc;
 
     const size_t smem_static = align_up(encode_static_smem(), 16);
-    const size_t dyn = c->smem_optin;
-    const size_t plane_cap = dyn - smem_static;
-    const int grid = (int)std::min<uint64_t>(std::max<uint64_t>(NF, 1), (uint64_t)c->sm_count);
+    size_t dyn = c->smem_optin;
+    size_t plane_cap = dyn - smem_static;
+    int ctas_per_sm = 1;
+    // Experiment knob: FLO_B200_GLOBAL_PLANES=<ctas per SM> keeps the sample planes in per-CTA global (L2)
+    // scratch instead of shared memory so that several smaller CTAs fit one SM.
+    if (const char *e = getenv("FLO_B200_GLOBAL_PLANES")) {
+        ctas_per_sm = std::max(1, atoi(e));
+        dyn = smem_static;
+        plane_cap = 0;
+    }
+    if (getenv("FLO_B200_DEBUG_OCC")) debug_occupancy(dyn);
+    const int grid = (int)std::min<uint64_t>(std::max<uint64_t>(NF, 1), (uint64_t)c->sm_count * ctas_per_sm);
     if ((rc = c->cres.reserve(sizeof(ChanResult) * 256ull * grid))) return rc;
     uint64_t plane_elems = 0;
     if (L.max_plane_elems * 2 > plane_cap) {

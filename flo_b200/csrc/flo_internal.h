@@ -95,5 +95,6 @@ cudaError_t launch_crc_segments(const FinalParams &p, cudaStream_t st);
 cudaError_t launch_headers(const FinalParams &p, cudaStream_t st);
 cudaError_t configure_encode_kernel(size_t dyn_smem);
 void upload_crc_tables();
+int debug_occupancy(size_t dyn_smem);
 
 }  // namespace flo

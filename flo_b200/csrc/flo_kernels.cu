@@ -19,6 +19,7 @@
 // Everything is integer-exact; the only floating point is the f32 quantiser
 // (one RN multiply) and the sequential f64 Levinson-Durbin recursion, both with
 // explicit _rn intrinsics so that no FMA contraction can change a bit.
+#include <cstdio>
 #include <type_traits>
 
 #include "flo_internal.h"
@@ -270,6 +271,17 @@ cudaError_t launch_headers(const FinalParams &p, cudaStream_t st) {
     if (p.n_tracks == 0) return cudaSuccess;
     k_write_headers<<<p.n_tracks, 128, 0, st>>>(p);
     return cudaGetLastError();
+}
+
+
+int debug_occupancy(size_t dyn_smem) {
+    int n = -1;
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, k_encode_frames<8>, NT, dyn_smem);
+    cudaFuncAttributes a;
+    cudaFuncGetAttributes(&a, k_encode_frames<8>);
+    printf("occupancy(NT=%d, dyn=%zu) = %d blocks/SM; regs=%d static_smem=%zu maxdyn=%d carveout=%d\n", NT, dyn_smem, n,
+           a.numRegs, a.sharedSizeBytes, a.maxDynamicSharedSizeBytes, a.preferredShmemCarveout);
+    return n;
 }
 
 }  // namespace flo
