@@ -200,11 +200,15 @@ def main() -> int:
     ctx.set_stream(stream.cuda_stream)
 
     # synthetic PCM directly in HBM (integer-only generator, identical to tests/helpers.synth_pcm16)
+    from flo_b200 import shard
     if world == 1:
-        tracks_n = [seconds * SR]
+        corpus_n = [seconds * SR]
     else:
-        tracks_n = [TRACK_SECONDS * SR] * (seconds // TRACK_SECONDS)
-    pcm_tracks = [synth_torch.synth_pcm16_long(n, CH, SR, SEED + 131 * (rank * len(tracks_n) + i), "multitone", 64, dev)
+        corpus_n = [TRACK_SECONDS * SR] * (world * (seconds // TRACK_SECONDS))      # the whole job's tracks
+    ranges = shard.partition_tracks([shard.frames_of_track(n * CH, SR, CH) for n in corpus_n], world)
+    t_lo, t_hi = ranges[rank]                                                       # this rank's contiguous shard
+    tracks_n = corpus_n[t_lo:t_hi]
+    pcm_tracks = [synth_torch.synth_pcm16_long(n, CH, SR, SEED + 131 * (t_lo + i), "multitone", 64, dev)
                   for i, n in enumerate(tracks_n)]
     f32_tracks = [p.to(torch.float32) * (1.0 / 32768.0) for p in pcm_tracks]    # reflo/src/audio.rs:247-254 (exact)
     n_list = [int(t.numel()) for t in f32_tracks]
@@ -212,14 +216,12 @@ def main() -> int:
     bound = ctx.output_bound(n_list, [SR] * len(n_list), [CH] * len(n_list))
     d_out = torch.empty(bound, dtype=torch.uint8, device=dev)
     ptrs = [t.data_ptr() for t in f32_tracks]
-    lens_buf = torch.zeros(world, dtype=torch.int64, device=dev)
 
     def step():
         off, ln = ctx.encode_batch_device(ptrs, n_list, [SR] * len(ptrs), [CH] * len(ptrs), [16] * len(ptrs),
                                           d_out.data_ptr(), bound, level=level)
-        if world > 1:       # per-shard byte lengths for the final concatenation (the only exchange)
-            mine = torch.tensor([int(ln.sum())], dtype=torch.int64, device=dev)
-            dist.all_gather_into_tensor(lens_buf, mine)
+        if world > 1:       # per-track byte lengths for the final concatenation (the only exchange)
+            shard.exchange_lengths([int(v) for v in ln], ranges, rank)
         return off, ln
 
     def sync_all():

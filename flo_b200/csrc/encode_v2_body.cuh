@@ -67,12 +67,14 @@ __device__ __forceinline__ void atomic_add64(u64 *p, u64 v) { atomicAdd(reinterp
 // scalar pieces of the reference
 // ----------------------------------------------------------------------------
 // f32_to_i32, core/audio_constants.rs:18-20: (x * 32767.0).clamp(-32768, 32767) as i32.
-// cvt.rzi saturates and maps NaN to 0 exactly like Rust's `as i32`; clamping the
-// truncated integer equals truncating the clamped float because both bounds are integers.
+// cvt.rzi.sat saturates and maps NaN to 0 exactly like Rust's `as i32`; saturating the
+// truncated value equals truncating the clamped float because both bounds are integers.
 __device__ __forceinline__ i32 f32_to_i32(float x) {
-    float y = __fmul_rn(x, 32767.0f);
-    int v = __float2int_rz(y);
-    return max(-32768, min(32767, v));
+    // one conversion instruction: round toward zero, saturate to [-32768, 32767], NaN -> 0
+    const float y = __fmul_rn(x, 32767.0f);
+    short v;
+    asm("cvt.rzi.sat.s16.f32 %0, %1;" : "=h"(v) : "f"(y));
+    return (i32)v;
 }
 // silence test of encoder.rs:70: |x| < 1e-7 (NaN is not silent)
 __device__ __forceinline__ bool is_loud(float x) { return !(fabsf(x) < 1e-7f); }
@@ -1169,11 +1171,14 @@ __global__ void __launch_bounds__(NT, FLO_MIN_CTAS) k_encode_frames(const Encode
                               ? smem_planes
                               : p.plane_scratch + (size_t)blockIdx.x * p.plane_scratch_elems;
 
+        const long long tcA = clock64();
         if (p.format == FLO_FMT_PCM16)
             ingest_frame<int16_t>(s, reinterpret_cast<const int16_t *>(tr.samples) + start, len, C, planes, stride);
         else
             ingest_frame<float>(s, reinterpret_cast<const float *>(tr.samples) + start, len, C, planes, stride);
+        const long long tcB = clock64();
         __syncthreads();
+        if (tid == 0) { atomicAdd(p.phase_cycles + 12, (u64)(tcA - tc0)); atomicAdd(p.phase_cycles + 13, (u64)(tcB - tcA)); }
 
         const u64 data_base = tr.static_off + FILE_HDR + 4ull + 20ull * tr.n_frames;   // writer.rs:51, 89-95
 
