@@ -290,3 +290,38 @@ def test_zero_copy_views_and_output_pool(fb, ctx):
             for a, b in zip(res.arrays, plain):
                 assert a.tobytes() == b
     check_same(plain[1], oracle.encode(specs[1].samples, sr, ch, 16, 5, b"m1"), "batch track 1")
+
+
+def test_config4_hires_max_order_properties(fb, ctx):
+    """BASELINE config 4 shape (96 kHz stereo, bit_depth 24 in the header, level 9 = LPC order 12) at 20 s:
+    frames do not fit shared memory (global-plane path); container invariants + decode round trip + spot frames."""
+    sr, ch, secs = 96000, 2, 20
+    pcm = synth_pcm16(sr * secs, ch, sr, seed=0xF13, kind="sweep", noise_lsb=32)
+    out = fb.Encoder(sr, ch, 24, context=ctx).with_compression(9).encode_pcm16(pcm, b"hires")
+    f = oracle.FloFile(out)
+    assert (f.sample_rate, f.channels, f.bit_depth, f.level, f.num_frames) == (sr, ch, 24, 9, secs)
+    assert zlib.crc32(f.data_chunk()) == f.crc32 and out.endswith(b"hires")
+    assert all(fr.frame_type in (12, 254) for fr in f.frames)
+    want = pcm.astype(np.int32) - np.sign(pcm).astype(np.int32)
+    assert np.array_equal(oracle.decode_i32(out), want)
+    for i in (0, 11, secs - 1):
+        seg = pcm[i * sr * ch:(i + 1) * sr * ch]
+        ref = oracle.FloFile(oracle.encode_pcm16(seg, sr, ch, 24, 9, b""))
+        assert f.frame_bytes(i) == ref.frame_bytes(0), f"frame {i}"
+
+
+def test_config5_many_short_tracks(fb, ctx):
+    """BASELINE config 5 shape (8 kHz mono speech-like, many short tracks) at 256 tracks x 3 s: the batch entry
+    against the oracle track by track (a quarter of them), plus CRC on all."""
+    sr, ntr = 8000, 256
+    specs = []
+    for t in range(ntr):
+        pcm = synth_pcm16(3 * sr + (t % 7) * 13, 1, sr, seed=0xF14 + t, kind="speech", noise_lsb=16)
+        specs.append(fb.TrackSpec(pcm, sr, 1, 16, b"t%03d" % t))
+    got = ctx.encode_batch(specs, 5, fb.FMT_PCM16)
+    assert len(got) == ntr
+    for t in range(ntr):
+        f = oracle.FloFile(got[t])
+        assert zlib.crc32(f.data_chunk()) == f.crc32 and f.num_frames == 4 - (t % 7 == 0)
+        if t % 4 == 0:
+            check_same(got[t], oracle.encode_pcm16(specs[t].samples, sr, 1, 16, 5, specs[t].metadata), f"track {t}")
