@@ -412,10 +412,16 @@ __device__ void pass1(Smem &s, int nch) {
                     for (int l = 0; l <= P; l++) acc[l] = __fma_rn(w[P + j], w[P + j - l], acc[l]);
                 }
             }
+            // samples are accumulated in pairs: one 3-input add (IADD3) and one 3-input OR (LOP3) per two samples
+            u32 p0 = 0, p1 = 0, p2 = 0, p3 = 0, p4 = 0;
             fixed_chunk(x + (NH - 4), i0 == 0, [&](int j, i32 r0, i32 r1, i32 r2, i32 r3, i32 r4) {
                 const u32 a0 = (u32)abs(r0), a1 = (u32)abs(r1), a2 = (u32)abs(r2), a3 = (u32)abs(r3), a4 = (u32)abs(r4);
-                fsum[0] += a0; fsum[1] += a1; fsum[2] += a2; fsum[3] += a3; fsum[4] += a4;
-                forr[0] |= a0; forr[1] |= a1; forr[2] |= a2; forr[3] |= a3; forr[4] |= a4;
+                if (j & 1) {
+                    fsum[0] += p0 + a0; fsum[1] += p1 + a1; fsum[2] += p2 + a2; fsum[3] += p3 + a3; fsum[4] += p4 + a4;
+                    forr[0] |= p0 | a0; forr[1] |= p1 | a1; forr[2] |= p2 | a2; forr[3] |= p3 | a3; forr[4] |= p4 | a4;
+                } else {
+                    p0 = a0; p1 = a1; p2 = a2; p3 = a3; p4 = a4;
+                }
             });
         },
         [&](int c, int i) {
@@ -472,11 +478,17 @@ __device__ void pass2(Smem &s, int nch) {
                 if (cs.lpc_ok[O - 5]) {
                     const int j0 = cs.lpc_j0[O - 5];
                     u32 sa = lsum[O - 5], t0 = lt0[O - 5], t1 = lt1[O - 5], orr = lorr[O - 5];
+                    u32 pa = 0, pw = 0, pv = 0;
                     lpc_chunk<O, P>(x, i0 == 0, cs.qd[O - 5], [&](int j, i32 r) {
                         const u32 a = (u32)abs(r);
                         const u32 ws = (a + (u32)(r >> 31)) >> j0;     // w = |r| - [r < 0]
-                        sa += a; orr |= a;
-                        t0 += ws; t1 += ws >> 1;
+                        const u32 wv = ws >> 1;
+                        if (j & 1) {                               // pairs: 3-input add / OR per two samples
+                            sa += pa + a; orr |= pa | a;
+                            t0 += pw + ws; t1 += pv + wv;
+                        } else {
+                            pa = a; pw = ws; pv = wv;
+                        }
                     });
                     lsum[O - 5] = sa; lt0[O - 5] = t0; lt1[O - 5] = t1; lorr[O - 5] = orr;
                 }
