@@ -1161,13 +1161,13 @@ __global__ void __launch_bounds__(NT, FLO_MIN_CTAS) k_encode_frames(const Encode
             // (look-back status) in nearly ticket order.  Taking tickets one frame ahead (to prefetch the next
             // frame's samples into L2) was tried: a CTA that lags then holds an early ticket for a whole frame
             // time and every later frame stalls in the look-back -- 1.4 ms -> 2.0 ms per 1184 frames.
-            s.g = atomicAdd(p.ticket, 1u);
+            s.g = p.frame_begin + atomicAdd(p.ticket, 1u);
             s.loud = 0; s.ms = 0;
             s.ms_var[0] = s.ms_var[1] = s.ms_var[2] = 0;
         }
         __syncthreads();
         const u32 g = s.g;
-        if (g >= p.n_frames) break;
+        if (g >= p.frame_end) break;
         const long long tc0 = clock64();
         const uint2 fd = p.frames[g];
         const TrackDev tr = p.tracks[fd.x];

@@ -88,6 +88,7 @@ struct HostBuf {                      // grow-only pinned host arena
 };
 
 inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+constexpr int MAX_WAVES = 16;
 
 // Pinned output blocks.  Large results are copied device -> host straight into one page-locked block
 // and handed out as pointers into it (no second host copy); flo_free() on the last pointer of a
@@ -161,7 +162,9 @@ struct flo_ctx {
     size_t smem_optin = 0;
     std::mutex mu;
     cudaStream_t own_stream = nullptr, stream = nullptr;
+    cudaStream_t s_in = nullptr, s_out = nullptr;          // copy streams of the pipelined host entry
     cudaEvent_t ev[8] = {};
+    cudaEvent_t ev_in[MAX_WAVES] = {}, ev_k[MAX_WAVES] = {}, ev_fin = nullptr;
     DevBuf in, out, meta, tracks, frames, ctrl, fexcl, fsize, foff, plane, cres, report;
     uint64_t counters[24] = {0};      // [0..7] analysis counters, [8..23] per-phase SM clock sums
     HostBuf h_small, h_out;
@@ -195,6 +198,11 @@ extern "C" int flo_ctx_create(int device, flo_ctx **out) {
     if (e2 != cudaSuccess) { set_err("cudaStreamCreate: %s", cudaGetErrorString(e2)); delete c; return FLO_ERR_CUDA; }
     c->stream = c->own_stream;
     for (auto &ev : c->ev) cudaEventCreate(&ev);
+    cudaStreamCreateWithFlags(&c->s_in, cudaStreamNonBlocking);
+    cudaStreamCreateWithFlags(&c->s_out, cudaStreamNonBlocking);
+    for (auto &ev : c->ev_in) cudaEventCreateWithFlags(&ev, cudaEventDisableTiming);
+    for (auto &ev : c->ev_k) cudaEventCreateWithFlags(&ev, cudaEventDisableTiming);
+    cudaEventCreateWithFlags(&c->ev_fin, cudaEventDisableTiming);
     upload_crc_tables();
     e2 = configure_encode_kernel(c->smem_optin);
     if (e2 != cudaSuccess) { set_err("cudaFuncSetAttribute(max dynamic smem %zu): %s", c->smem_optin, cudaGetErrorString(e2)); flo_ctx_destroy(c); return FLO_ERR_CUDA; }
@@ -214,6 +222,11 @@ extern "C" void flo_ctx_destroy(flo_ctx *c) {
     c->h_small.release();
     c->h_out.release();
     for (auto &ev : c->ev) if (ev) cudaEventDestroy(ev);
+    for (auto &ev : c->ev_in) if (ev) cudaEventDestroy(ev);
+    for (auto &ev : c->ev_k) if (ev) cudaEventDestroy(ev);
+    if (c->ev_fin) cudaEventDestroy(c->ev_fin);
+    if (c->s_in) cudaStreamDestroy(c->s_in);
+    if (c->s_out) cudaStreamDestroy(c->s_out);
     if (c->own_stream) cudaStreamDestroy(c->own_stream);
     delete c;
 }
@@ -335,8 +348,11 @@ extern "C" size_t flo_output_bound(const flo_track *tracks, size_t n_tracks) {
 }
 
 // ---- the batch pass ----------------------------------------------------------------
+// `sink` (host entry only): when non-null and the batch is large, the images are copied to a pinned host block
+// while later waves are still being uploaded and encoded; *sink receives the block (its data is complete on return).
 static int encode_batch_impl(flo_ctx *c, const flo_track *tracks, size_t n_tracks, int format, uint8_t level,
-                             bool host_inputs, void *d_out, size_t d_out_cap, uint64_t *offsets, uint64_t *lens) {
+                             bool host_inputs, void *d_out, size_t d_out_cap, uint64_t *offsets, uint64_t *lens,
+                             OutBlock **sink = nullptr) {
     if (format != FLO_FMT_F32 && format != FLO_FMT_PCM16) { set_err("unknown sample format %d", format); return FLO_ERR_ARG; }
     if (n_tracks == 0) return FLO_OK;
     if (level > 9) level = 9;                                          // with_compression, encoder.rs:26-29
@@ -358,7 +374,7 @@ static int encode_batch_impl(flo_ctx *c, const flo_track *tracks, size_t n_track
     const uint32_t NF = (uint32_t)L.n_frames, NSEG = (uint32_t)L.n_segs, NTR = (uint32_t)n_tracks;
     if ((rc = c->tracks.reserve(sizeof(TrackDev) * n_tracks))) return rc;
     if ((rc = c->frames.reserve(sizeof(uint2) * std::max<uint64_t>(NF, 1)))) return rc;
-    const size_t ctrl_bytes = 8ull * NF + 256 + 4ull * n_tracks;       // status words, ticket, err, counters, phase clocks, track CRCs
+    const size_t ctrl_bytes = 8ull * NF + 256 + 4ull * n_tracks + 4ull * MAX_WAVES;       // status words, ticket, err, counters, phase clocks, track CRCs
     if ((rc = c->ctrl.reserve(ctrl_bytes))) return rc;
     if ((rc = c->fexcl.reserve(8ull * std::max<uint64_t>(NF, 1)))) return rc;
     if ((rc = c->fsize.reserve(4ull * std::max<uint64_t>(NF, 1)))) return rc;
@@ -390,23 +406,28 @@ static int encode_batch_impl(flo_ctx *c, const flo_track *tracks, size_t n_track
         c->report_frames = NF;
     }
 
-    // inputs
+    // ---- wave plan: the host entry uploads and encodes the batch in waves of whole frames so that the
+    // H2D copy of wave w+1 overlaps the encode kernel of wave w (frames are independent; the look-back
+    // status words carry the running byte offset from one launch to the next).
+    int n_waves = 1;
+    if (host_inputs && NF >= 2u * (uint32_t)grid * 2u) n_waves = (int)std::min<uint32_t>(MAX_WAVES, NF / (3u * (uint32_t)grid));
+    if (n_waves < 1) n_waves = 1;
+    std::vector<uint32_t> wave_end(n_waves);
+    for (int w = 0; w < n_waves; w++) wave_end[w] = (uint32_t)((uint64_t)NF * (w + 1) / n_waves);
+    const bool piped = n_waves > 1;
+    cudaStream_t s_in = piped ? c->s_in : st;
+
+    // small tables through pinned staging
     CK(cudaEventRecord(c->ev[0], st));
     if (host_inputs) {
         if ((rc = c->in.reserve(std::max<uint64_t>(L.in_bytes, 1)))) return rc;
-        for (size_t t = 0; t < n_tracks; t++) {
-            L.tr[t].samples = (const uint8_t *)c->in.p + L.in_off[t];
-            if (tracks[t].n_interleaved)
-                CK(cudaMemcpyAsync((uint8_t *)c->in.p + L.in_off[t], tracks[t].samples, tracks[t].n_interleaved * esz,
-                                   cudaMemcpyHostToDevice, st));
-        }
+        for (size_t t = 0; t < n_tracks; t++) L.tr[t].samples = (const uint8_t *)c->in.p + L.in_off[t];
     } else {
         for (size_t t = 0; t < n_tracks; t++) {
             L.tr[t].samples = tracks[t].samples;
             if (((uintptr_t)tracks[t].samples & (esz - 1)) != 0) { set_err("track %zu: device samples pointer not aligned to the sample size", t); return FLO_ERR_ARG; }
         }
     }
-    // small tables through pinned staging
     uint8_t *hs = (uint8_t *)c->h_small.p;
     memcpy(hs, L.tr.data(), sizeof(TrackDev) * n_tracks);
     uint8_t *hmeta = hs + sizeof(TrackDev) * n_tracks;
@@ -415,7 +436,6 @@ static int encode_batch_impl(flo_ctx *c, const flo_track *tracks, size_t n_track
     CK(cudaMemcpyAsync(c->tracks.p, hs, sizeof(TrackDev) * n_tracks, cudaMemcpyHostToDevice, st));
     if (L.meta_total) CK(cudaMemcpyAsync(c->meta.p, hmeta, L.meta_total, cudaMemcpyHostToDevice, st));
     CK(cudaMemsetAsync(c->ctrl.p, 0, ctrl_bytes, st));
-    CK(cudaEventRecord(c->ev[1], st));
 
     uint32_t launches = 0;
     EncodeParams ep;
@@ -427,10 +447,11 @@ static int encode_batch_impl(flo_ctx *c, const flo_track *tracks, size_t n_track
     ep.level = level;
     ep.out = out;
     ep.status = (unsigned long long *)c->ctrl.p;
-    ep.ticket = (uint32_t *)((uint8_t *)c->ctrl.p + 8ull * NF);
-    ep.err = ep.ticket + 1;
-    ep.counters = ep.ticket + 2;
-    ep.phase_cycles = (unsigned long long *)(ep.ticket + 16);
+    uint32_t *ctl = (uint32_t *)((uint8_t *)c->ctrl.p + 8ull * NF);
+    ep.err = ctl + 1;
+    ep.counters = ctl + 2;
+    ep.phase_cycles = (unsigned long long *)(ctl + 16);
+    uint32_t *wave_ticket = ctl + 48 + n_tracks;
     ep.frame_excl = (unsigned long long *)c->fexcl.p;
     ep.frame_size = (uint32_t *)c->fsize.p;
     ep.plane_scratch = (int16_t *)c->plane.p;
@@ -444,15 +465,75 @@ static int encode_batch_impl(flo_ctx *c, const flo_track *tracks, size_t n_track
     fp.tracks = ep.tracks; fp.n_tracks = NTR; fp.n_frames = NF; fp.level = level; fp.frames = ep.frames;
     fp.out = out; fp.meta = (const uint8_t *)c->meta.p;
     fp.frame_excl = ep.frame_excl; fp.frame_size = ep.frame_size;
-    fp.track_crc = ep.ticket + 48; fp.n_segs = NSEG;
+    fp.track_crc = ctl + 48; fp.n_segs = NSEG;
     fp.file_off = (unsigned long long *)c->foff.p;
     fp.file_len = fp.file_off + n_tracks;
 
     CK(launch_setup(ep.tracks, NTR, (uint2 *)c->frames.p, NF, st));
     launches += NF ? 1 : 0;
+    CK(cudaEventRecord(c->ev[1], st));
+    if (piped) { CK(cudaEventRecord(c->ev_fin, st)); CK(cudaStreamWaitEvent(s_in, c->ev_fin, 0)); }   // arenas are reused across calls
+
+    // per-wave D2H sink (few tracks only: header/TOC/metadata regions are copied one by one at the end)
+    OutBlock *blk = nullptr;
+    const bool sink_on = sink && piped && n_tracks <= 16 && L.out_bound >= SMALL_OUTPUT;
+    struct WaveEnd { unsigned long long excl; uint32_t size; uint32_t pad; };
+    WaveEnd *h_wave = nullptr;
+    if (sink_on) {
+        blk = take_block(L.out_bound);
+        if (!blk) { set_err("cudaMallocHost(%llu) failed for the output block", (unsigned long long)L.out_bound); return FLO_ERR_NOMEM; }
+        if ((rc = c->h_out.reserve(sizeof(WaveEnd) * MAX_WAVES + 64))) { drop_block(blk); return rc; }
+        h_wave = (WaveEnd *)c->h_out.p;
+    }
+    auto fail = [&](cudaError_t e, const char *what) {
+        cudaDeviceSynchronize();
+        if (blk) drop_block(blk);
+        set_err("%s: %s", what, cudaGetErrorString(e));
+        return FLO_ERR_CUDA;
+    };
+
+    // track cursor for the per-wave sample copies
+    size_t tcur = 0;
     CK(cudaEventRecord(c->ev[2], st));
-    CK(launch_encode(ep, grid, dyn, st));
-    launches += NF ? 1 : 0;
+    uint32_t g0 = 0;
+    for (int w = 0; w < n_waves; w++) {
+        const uint32_t g1 = wave_end[w];
+        if (host_inputs) {
+            // samples of frames [g0, g1): per track the frames [max(g0, first) - first, min(g1, first + nf) - first)
+            for (size_t t = tcur; t < n_tracks; t++) {
+                const TrackDev &d = L.tr[t];
+                const uint64_t f_lo = std::max<uint64_t>(g0, d.first_frame), f_hi = std::min<uint64_t>(g1, (uint64_t)d.first_frame + d.n_frames);
+                if (d.first_frame >= g1 && d.n_frames) break;
+                if (d.n_frames == 0 || f_hi <= f_lo) { if ((uint64_t)d.first_frame + d.n_frames <= g1) tcur = t + 1; continue; }
+                const uint64_t spf = (uint64_t)d.sample_rate * d.channels;
+                const uint64_t e_lo = (f_lo - d.first_frame) * spf;
+                const uint64_t e_hi = (f_hi == (uint64_t)d.first_frame + d.n_frames) ? d.n_inter : (f_hi - d.first_frame) * spf;
+                cudaError_t e = cudaMemcpyAsync((uint8_t *)c->in.p + L.in_off[t] + e_lo * esz,
+                                                (const uint8_t *)tracks[t].samples + e_lo * esz, (e_hi - e_lo) * esz,
+                                                cudaMemcpyHostToDevice, s_in);
+                if (e != cudaSuccess) return fail(e, "H2D of the samples failed");
+                if ((uint64_t)d.first_frame + d.n_frames <= g1) tcur = t + 1;
+            }
+            if (piped) {
+                cudaError_t e = cudaEventRecord(c->ev_in[w], s_in);
+                if (e == cudaSuccess) e = cudaStreamWaitEvent(st, c->ev_in[w], 0);
+                if (e != cudaSuccess) return fail(e, "stream ordering failed");
+            }
+        }
+        ep.frame_begin = g0; ep.frame_end = g1; ep.ticket = n_waves > 1 ? wave_ticket + w : ctl;
+        {
+            cudaError_t e = launch_encode(ep, grid, dyn, st);
+            if (e != cudaSuccess) return fail(e, "encode kernel launch failed");
+            launches += g1 > g0 ? 1 : 0;
+        }
+        if (sink_on && g1 > g0) {
+            cudaError_t e = cudaMemcpyAsync(&h_wave[w].excl, ep.frame_excl + (g1 - 1), 8, cudaMemcpyDeviceToHost, st);
+            if (e == cudaSuccess) e = cudaMemcpyAsync(&h_wave[w].size, ep.frame_size + (g1 - 1), 4, cudaMemcpyDeviceToHost, st);
+            if (e == cudaSuccess) e = cudaEventRecord(c->ev_k[w], st);
+            if (e != cudaSuccess) return fail(e, "wave bookkeeping failed");
+        }
+        g0 = g1;
+    }
     CK(cudaEventRecord(c->ev[3], st));
     CK(launch_toc(fp, st));
     launches += NF ? 1 : 0;
@@ -464,16 +545,53 @@ static int encode_batch_impl(flo_ctx *c, const flo_track *tracks, size_t n_track
     launches += 1;
     CK(cudaEventRecord(c->ev[6], st));
 
+    if (sink_on) {
+        // DATA bytes of each wave leave the device as soon as its kernel is done, on their own stream
+        auto data_base = [&](uint32_t g) {           // file position of the DATA chunk of the track that owns frame g
+            size_t lo = 0, hi = n_tracks;
+            while (hi - lo > 1) { size_t mid = (lo + hi) / 2; if (L.tr[mid].first_frame <= g) lo = mid; else hi = mid; }
+            return L.tr[lo].static_off + FILE_HDR + 4 + 20ull * L.tr[lo].n_frames;
+        };
+        uint64_t cur = NF ? data_base(0) : 0;
+        uint32_t gp = 0;
+        for (int w = 0; w < n_waves; w++) {
+            const uint32_t g1 = wave_end[w];
+            if (g1 == gp) continue;
+            cudaError_t e = cudaEventSynchronize(c->ev_k[w]);
+            if (e != cudaSuccess) return fail(e, "wave synchronisation failed");
+            const uint64_t end = data_base(g1 - 1) + h_wave[w].excl + h_wave[w].size;
+            if (end > cur) {
+                e = cudaMemcpyAsync(blk->base + cur, out + cur, end - cur, cudaMemcpyDeviceToHost, c->s_out);
+                if (e != cudaSuccess) return fail(e, "D2H of a wave failed");
+            }
+            cur = end;
+            gp = g1;
+        }
+    }
     // results: per-track offsets/lengths + error flag
     uint64_t *h_off = (uint64_t *)(hs + align_up(sizeof(TrackDev) * n_tracks + L.meta_total, 16));
     uint32_t *h_err = (uint32_t *)(h_off + 2 * n_tracks);           // err + 8 counters
     CK(cudaMemcpyAsync(h_off, c->foff.p, 16ull * n_tracks, cudaMemcpyDeviceToHost, st));
     CK(cudaMemcpyAsync(h_err, ep.err, 4 * 47, cudaMemcpyDeviceToHost, st));   // err, counters[8], pad, phase clocks[16]
     CK(cudaStreamSynchronize(st));
-    if (*h_err) { set_err("device-side consistency check failed (code 0x%08x)", *h_err); return FLO_ERR_INTERNAL; }
+    if (*h_err) { if (blk) { cudaDeviceSynchronize(); drop_block(blk); } set_err("device-side consistency check failed (code 0x%08x)", *h_err); return FLO_ERR_INTERNAL; }
     for (size_t t = 0; t < n_tracks; t++) { offsets[t] = h_off[t]; lens[t] = h_off[n_tracks + t]; }
     for (int i = 0; i < 8; i++) c->counters[i] = h_err[1 + i];
     for (int i = 0; i < 16; i++) memcpy(&c->counters[8 + i], &h_err[15 + 2 * i], 8);
+    if (sink_on) {
+        // header + TOC in front of each DATA chunk and the metadata behind it were written by the final kernels
+        for (size_t t = 0; t < n_tracks; t++) {
+            const uint64_t head = FILE_HDR + 4 + 20ull * L.tr[t].n_frames;
+            cudaError_t e = cudaMemcpyAsync(blk->base + offsets[t], out + offsets[t], head, cudaMemcpyDeviceToHost, c->s_out);
+            if (e == cudaSuccess && L.tr[t].meta_len)
+                e = cudaMemcpyAsync(blk->base + offsets[t] + lens[t] - L.tr[t].meta_len, out + offsets[t] + lens[t] - L.tr[t].meta_len,
+                                    L.tr[t].meta_len, cudaMemcpyDeviceToHost, c->s_out);
+            if (e != cudaSuccess) return fail(e, "D2H of a header failed");
+        }
+        cudaError_t e = cudaStreamSynchronize(c->s_out);
+        if (e != cudaSuccess) return fail(e, "D2H synchronisation failed");
+        *sink = blk;
+    }
 
     float t_all = 0, t_enc = 0, t_toc = 0, t_crc = 0, t_hdr = 0, t_setup = 0, t_h2d = 0;
     cudaEventElapsedTime(&t_h2d, c->ev[0], c->ev[1]);
@@ -502,8 +620,14 @@ extern "C" int flo_encode_batch(flo_ctx *c, const flo_track *tracks, size_t n_tr
     for (size_t t = 0; t < n_tracks; t++) { outs[t].data = nullptr; outs[t].len = 0; }
     if (n_tracks == 0) return FLO_OK;
     std::vector<uint64_t> off(n_tracks), len(n_tracks);
-    int rc = encode_batch_impl(c, tracks, n_tracks, format, level, true, nullptr, 0, off.data(), len.data());
+    OutBlock *piped = nullptr;
+    int rc = encode_batch_impl(c, tracks, n_tracks, format, level, true, nullptr, 0, off.data(), len.data(), &piped);
     if (rc) return rc;
+    if (piped) {                       // the images already sit in a pinned block (copied out wave by wave)
+        for (size_t t = 0; t < n_tracks; t++) { outs[t].data = piped->base + off[t]; outs[t].len = (size_t)len[t]; }
+        publish_block(piped, n_tracks);
+        return FLO_OK;
+    }
     // one D2H of the compact image region, then split per track
     uint64_t total = 0;
     for (size_t t = 0; t < n_tracks; t++) total = std::max(total, off[t] + len[t]);

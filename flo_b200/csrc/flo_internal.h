@@ -52,11 +52,12 @@ struct EncodeParams {
     const TrackDev *tracks;
     const uint2 *frames;              // per global frame: {track, frame index in track}
     uint32_t n_frames;
+    uint32_t frame_begin, frame_end;  // this launch encodes global frames [frame_begin, frame_end)
     int format;                       // FLO_FMT_*
     int level;                        // 0..9
     uint8_t *out;                     // output arena
     unsigned long long *status;       // decoupled look-back words, one per frame (zeroed)
-    uint32_t *ticket;                 // dynamic frame counter (zeroed)
+    uint32_t *ticket;                 // dynamic frame counter of this launch (zeroed): next frame = frame_begin + ticket++
     unsigned long long *frame_excl;   // out: exclusive prefix of frame sizes (global)
     uint32_t *frame_size;             // out
     int16_t *plane_scratch;           // per-CTA global sample planes for frames too large for shared memory

@@ -245,7 +245,7 @@ cudaError_t launch_setup(const TrackDev *tracks, uint32_t n_tracks, uint2 *frame
     return cudaGetLastError();
 }
 cudaError_t launch_encode(const EncodeParams &p, int grid, size_t dyn_smem, cudaStream_t st) {
-    if (p.n_frames == 0) return cudaSuccess;
+    if (p.frame_end <= p.frame_begin) return cudaSuccess;
     // one instantiation per LPC max order (encoder.rs:289-302); levels 0-3 never try LPC (encoder.rs:204)
     switch (p.level) {
         case 4: k_encode_frames<6><<<grid, NT, dyn_smem, st>>>(p); break;

@@ -325,3 +325,23 @@ def test_config5_many_short_tracks(fb, ctx):
         assert zlib.crc32(f.data_chunk()) == f.crc32 and f.num_frames == 4 - (t % 7 == 0)
         if t % 4 == 0:
             check_same(got[t], oracle.encode_pcm16(specs[t].samples, sr, 1, 16, 5, specs[t].metadata), f"track {t}")
+
+
+def test_pipelined_host_entry_matches_oracle(fb, ctx):
+    """Batches of >= 592 frames go through the wave pipeline (H2D / encode / D2H overlapped, look-back carried
+    across launches): one long track, and several tracks whose boundaries fall inside waves."""
+    sr = 8000
+    pcm = synth_pcm16(700 * sr + 123, 1, sr, seed=0xF15, kind="speech", noise_lsb=16)
+    got = fb.Encoder(sr, 1, 16, context=ctx).encode_pcm16(pcm, b"long")
+    check_same(got, oracle.encode_pcm16(pcm, sr, 1, 16, 5, b"long"), "700-frame track")
+    specs, want = [], []
+    for i, secs in enumerate((251, 3, 0, 330, 97)):
+        p = synth_pcm16(secs * sr + 7 * i, 2, sr, seed=0xF16 + i, kind="multitone", noise_lsb=32)
+        specs.append(fb.TrackSpec(pcm16_to_f32(p), sr, 2, 16, b"trk%d" % i))
+        want.append(oracle.encode(specs[-1].samples, sr, 2, 16, 5, specs[-1].metadata))
+    got = ctx.encode_batch(specs, 5)
+    for i, (g, w) in enumerate(zip(got, want)):
+        check_same(g, w, f"piped track {i}")
+    with ctx.encode_batch(specs, 5, views=True) as res:
+        for a, w in zip(res.arrays, want):
+            assert a.tobytes() == w
