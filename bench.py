@@ -317,6 +317,24 @@ def main() -> int:
         e2e = {"value": 2.0 * total_inter * world / float(tm.item()) / 1e9, "unit": "GB/s",
                "h2d_bytes_per_step": 4 * total_inter, "d2h_bytes_per_step": e2e_out,
                "ms_per_step": float(tm.item()) * 1e3, "x_realtime": seconds * world / float(tm.item())}
+        if extras is not None and world == 1:
+            # same call with reflo's 16-bit PCM as the host buffer (flo_encode_pcm16): half the H2D bytes
+            host_pcm = [torch.empty(n, dtype=torch.int16, pin_memory=True) for n in n_list]
+            for h, d in zip(host_pcm, pcm_tracks):
+                h.copy_(d)
+            torch.cuda.synchronize()
+            specs16 = [flo_b200.TrackSpec(h.numpy(), SR, CH, 16, b"") for h in host_pcm]
+            for _ in range(2):
+                with ctx.encode_batch(specs16, level, flo_b200.FMT_PCM16, views=True) as res:
+                    same = res.total_bytes() == e2e_out
+            t0 = time.perf_counter()
+            for _ in range(reps):
+                with ctx.encode_batch(specs16, level, flo_b200.FMT_PCM16, views=True) as res:
+                    pass
+            dt16 = (time.perf_counter() - t0) / reps
+            extras["e2e_pcm16_entry"] = {"value": 2.0 * total_inter / dt16 / 1e9, "unit": "GB/s", "ms_per_step": dt16 * 1e3,
+                                         "h2d_bytes_per_step": 2 * total_inter, "same_bytes_as_f32_entry": bool(same)}
+            del host_pcm, specs16
         del host_in, specs
 
     cpu = None

@@ -916,7 +916,9 @@ __device__ void pack_channel(Smem &s, const ChanState &cs, const ChanResult &cr,
             __syncthreads();
             if (tid == 0) { const long long pk3 = clock64(); atomicAdd(phase + 5, (u64)(pk1 - pk0)); atomicAdd(phase + 6, (u64)(pk2 - pk1)); atomicAdd(phase + 7, (u64)(pk3 - pk2)); }
             const u32 wend = (u32)(end_sc >> 5);
+            const long long pk4 = clock64();
             flush_ring(s.ring, obase, abase, lo, hi, wlo, wend);
+            if (tid == 0) atomicAdd(phase + 14, (u64)(clock64() - pk4));
             wlo = wend;
         } else {
             for (;;) {
