@@ -13,7 +13,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 SO = os.path.join(HERE, "libflo_b200.so")
-SOURCES = ["flo_kernels.cu", "flo_api.cu"]
+SOURCES = ["flo_encode_nt512.cu", "flo_encode_nt256.cu", "flo_encode_nt128.cu", "flo_kernels.cu", "flo_api.cu"]
 HEADERS = [os.path.join(CSRC, "flo_internal.h"), os.path.join(CSRC, "encode_v2_body.cuh"), os.path.join(os.path.dirname(HERE), "include", "flo_b200.h")]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
@@ -40,16 +40,20 @@ def build(force: bool = False, verbose: bool = False, defines: tuple = (), out: 
     """defines/out are for experiments (e.g. defines=("FLO_NT=1024",), out=".../libflo_b200_x.so")."""
     if not force and not stale() and out == SO:
         return SO
-    objs = []
+    from concurrent.futures import ThreadPoolExecutor
     tag = "" if out == SO else "_" + os.path.basename(out).replace(".so", "")
-    for src in SOURCES:
+
+    def compile_one(src: str) -> str:
         obj = os.path.join(CSRC, src.replace(".cu", tag + ".o"))
         cmd = [nvcc(), *NVCC_FLAGS, *[f"-D{d}" for d in defines], "-c", os.path.join(CSRC, src), "-o", obj]
         if verbose:
             cmd.insert(1, "-Xptxas=-v")
             print(" ".join(cmd))
         subprocess.check_call(cmd)
-        objs.append(obj)
+        return obj
+
+    with ThreadPoolExecutor(len(SOURCES)) as ex:          # the three kernel variants dominate: build them side by side
+        objs = list(ex.map(compile_one, SOURCES))
     cmd = [nvcc(), "-shared", "-o", out, *objs, "-cudart", "static"]
     subprocess.check_call(cmd)
     return out

@@ -1,3 +1,8 @@
+// This file is the body of one build variant of the frame-encode kernel: it is included by
+// flo_encode_nt{512,256,128}.cu inside namespace flo::FLO_VARIANT_NS with FLO_VARIANT_NT threads per CTA.
+constexpr int NT = FLO_VARIANT_NT;
+constexpr int NWARP = NT / 32;
+
 // ----------------------------------------------------------------------------
 // shared state of the frame-encode CTA
 // ----------------------------------------------------------------------------
@@ -54,7 +59,7 @@ struct Smem {
     u32 ring[RING_WORDS];             // bit-packer staging ring (big-endian bit order words)
 };
 
-size_t encode_static_smem() { return sizeof(Smem); }
+static size_t encode_static_smem() { return sizeof(Smem); }
 
 __device__ __forceinline__ u64 warp_sum64(u64 v) {
 #pragma unroll
@@ -228,13 +233,14 @@ __device__ __forceinline__ void unpack8(const int4 v, i32 *t) {
 }
 template <int NH>
 __device__ __forceinline__ void load_plane(const int16_t *pl, int i0, i32 (&x)[NH + CH]) {
-    i32 t[32];
+    static_assert(CH == 8 || CH == 16, "chunk of 8 or 16 samples");
+    i32 t[16 + CH];                                    // [0,16): up to 16 samples of history, [16, 16+CH): the chunk
     const int4 *p = reinterpret_cast<const int4 *>(pl + i0);
     const int4 z = make_int4(0, 0, 0, 0);
     unpack8(p[0], t + 16);
-    unpack8(p[1], t + 24);
-    if (NH > 8) unpack8(i0 > 0 ? p[-2] : z, t);
-    if (NH > 0) unpack8(i0 > 0 ? p[-1] : z, t + 8);
+    if (CH == 16) unpack8(p[1], t + 24);
+    if (NH > 8) unpack8(i0 >= 16 ? p[-2] : z, t);
+    if (NH > 0) unpack8(i0 >= 8 ? p[-1] : z, t + 8);
 #pragma unroll
     for (int i = 0; i < NH + CH; i++) x[i] = t[16 - NH + i];
 }
@@ -1138,11 +1144,8 @@ __device__ void ingest_frame(Smem &s, const T *in, u32 len, u32 C, int16_t *plan
 // ----------------------------------------------------------------------------
 extern __shared__ __align__(16) unsigned char dyn_smem[];
 
-#ifndef FLO_MIN_CTAS
-#define FLO_MIN_CTAS 1
-#endif
 template <int P>
-__global__ void __launch_bounds__(NT, FLO_MIN_CTAS) k_encode_frames(const EncodeParams p) {
+__global__ void __launch_bounds__(NT, FLO_VARIANT_CTAS) k_encode_frames(const EncodeParams p) {
     Smem &s = *reinterpret_cast<Smem *>(dyn_smem);
     int16_t *smem_planes = reinterpret_cast<int16_t *>(dyn_smem + ((sizeof(Smem) + 15) & ~size_t(15)));
     const int tid = threadIdx.x;
@@ -1397,4 +1400,33 @@ __global__ void __launch_bounds__(NT, FLO_MIN_CTAS) k_encode_frames(const Encode
     }
     __syncthreads();
     if (tid < 8 && s.cnt[tid]) atomicAdd(p.counters + tid, s.cnt[tid]);
+}
+
+// ----------------------------------------------------------------------------
+// launch glue of this variant
+// ----------------------------------------------------------------------------
+static cudaError_t variant_configure(size_t dyn_smem) {
+    cudaError_t e;
+    if ((e = cudaFuncSetAttribute(k_encode_frames<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn_smem))) return e;
+    if ((e = cudaFuncSetAttribute(k_encode_frames<6>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn_smem))) return e;
+    if ((e = cudaFuncSetAttribute(k_encode_frames<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn_smem))) return e;
+    if ((e = cudaFuncSetAttribute(k_encode_frames<10>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn_smem))) return e;
+    return cudaFuncSetAttribute(k_encode_frames<12>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn_smem);
+}
+static cudaError_t variant_launch(const EncodeParams &p, int grid, size_t dyn_smem, cudaStream_t st) {
+    if (p.frame_end <= p.frame_begin) return cudaSuccess;
+    // one instantiation per LPC max order (encoder.rs:289-302); levels 0-3 never try LPC (encoder.rs:204)
+    switch (p.level) {
+        case 4: k_encode_frames<6><<<grid, NT, dyn_smem, st>>>(p); break;
+        case 5: case 6: k_encode_frames<8><<<grid, NT, dyn_smem, st>>>(p); break;
+        case 7: k_encode_frames<10><<<grid, NT, dyn_smem, st>>>(p); break;
+        case 8: case 9: k_encode_frames<12><<<grid, NT, dyn_smem, st>>>(p); break;
+        default: k_encode_frames<0><<<grid, NT, dyn_smem, st>>>(p); break;
+    }
+    return cudaGetLastError();
+}
+static int variant_occupancy(size_t dyn_smem) {
+    int n = -1;
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, k_encode_frames<8>, NT, dyn_smem);
+    return n;
 }

@@ -204,8 +204,10 @@ extern "C" int flo_ctx_create(int device, flo_ctx **out) {
     for (auto &ev : c->ev_k) cudaEventCreateWithFlags(&ev, cudaEventDisableTiming);
     cudaEventCreateWithFlags(&c->ev_fin, cudaEventDisableTiming);
     upload_crc_tables();
-    e2 = configure_encode_kernel(c->smem_optin);
-    if (e2 != cudaSuccess) { set_err("cudaFuncSetAttribute(max dynamic smem %zu): %s", c->smem_optin, cudaGetErrorString(e2)); flo_ctx_destroy(c); return FLO_ERR_CUDA; }
+    for (int th : {512, 256, 128}) {
+        e2 = encode_variant(th).configure(c->smem_optin / encode_variant(th).ctas_per_sm - (encode_variant(th).ctas_per_sm > 1 ? 1024 : 0));
+        if (e2 != cudaSuccess) { set_err("cudaFuncSetAttribute(max dynamic smem): %s", cudaGetErrorString(e2)); flo_ctx_destroy(c); return FLO_ERR_CUDA; }
+    }
     e2 = cudaDeviceSynchronize();
     if (e2 != cudaSuccess) { set_err("device init: %s", cudaGetErrorString(e2)); flo_ctx_destroy(c); return FLO_ERR_CUDA; }
     *out = c;
@@ -382,18 +384,25 @@ static int encode_batch_impl(flo_ctx *c, const flo_track *tracks, size_t n_track
     if ((rc = c->meta.reserve(std::max<uint64_t>(L.meta_total, 1)))) return rc;
     if ((rc = c->h_small.reserve(sizeof(TrackDev) * n_tracks + L.meta_total + 16ull * n_tracks + 256))) return rc;
 
-    const size_t smem_static = align_up(encode_static_smem(), 16);
-    size_t dyn = c->smem_optin;
-    size_t plane_cap = dyn - smem_static;
-    int ctas_per_sm = 1;
-    // Experiment knob: FLO_B200_GLOBAL_PLANES=<ctas per SM> keeps the sample planes in per-CTA global (L2)
-    // scratch instead of shared memory so that several smaller CTAs fit one SM.
-    if (const char *e = getenv("FLO_B200_GLOBAL_PLANES")) {
-        ctas_per_sm = std::max(1, atoi(e));
-        dyn = smem_static;
-        plane_cap = 0;
-    }
-    if (getenv("FLO_B200_DEBUG_OCC")) debug_occupancy(dyn);
+    // Kernel variant: several small CTAs per SM when the largest frame's 16-bit planes fit the smaller share of
+    // shared memory (small frames are dominated by per-frame serial sections, which then overlap); one 512-thread
+    // CTA per SM for frames up to 48 kHz stereo; frames larger than that keep their planes in L2 and run as
+    // 2 x 256 threads.  FLO_B200_VARIANT=512|256|128 forces a variant (tests).
+    const size_t plane_bytes = L.max_plane_elems * 2;
+    auto share_of = [&](const EncodeVariant &v) { return v.ctas_per_sm > 1 ? c->smem_optin / v.ctas_per_sm - 1024 : c->smem_optin; };
+    auto fits = [&](const EncodeVariant &v) { return align_up(v.static_smem(), 16) + plane_bytes <= share_of(v); };
+    const EncodeVariant *var = &encode_variant(512);
+    if (fits(encode_variant(128))) var = &encode_variant(128);
+    else if (fits(encode_variant(256))) var = &encode_variant(256);
+    else if (!fits(encode_variant(512))) var = &encode_variant(256);      // planes in global scratch either way
+    if (const char *e = getenv("FLO_B200_VARIANT")) var = &encode_variant(atoi(e));
+    const size_t smem_static = align_up(var->static_smem(), 16);
+    size_t dyn, plane_cap;
+    if (fits(*var)) { dyn = share_of(*var); plane_cap = dyn - smem_static; }
+    else { dyn = smem_static; plane_cap = 0; }                            // global (L2) planes
+    const int ctas_per_sm = var->ctas_per_sm;
+    if (getenv("FLO_B200_DEBUG_OCC"))
+        fprintf(stderr, "flo_b200: variant %d x %d, dyn smem %zu, occupancy %d\n", var->threads, ctas_per_sm, dyn, var->occupancy(dyn));
     const int grid = (int)std::min<uint64_t>(std::max<uint64_t>(NF, 1), (uint64_t)c->sm_count * ctas_per_sm);
     if ((rc = c->cres.reserve(sizeof(ChanResult) * 256ull * grid))) return rc;
     uint64_t plane_elems = 0;
@@ -522,7 +531,7 @@ static int encode_batch_impl(flo_ctx *c, const flo_track *tracks, size_t n_track
         }
         ep.frame_begin = g0; ep.frame_end = g1; ep.ticket = n_waves > 1 ? wave_ticket + w : ctl;
         {
-            cudaError_t e = launch_encode(ep, grid, dyn, st);
+            cudaError_t e = var->launch(ep, grid, dyn, st);
             if (e != cudaSuccess) return fail(e, "encode kernel launch failed");
             launches += g1 > g0 ? 1 : 0;
         }

@@ -1,0 +1,25 @@
+// flo_encode_nt256.cu -- the frame-encode kernel built for 256 threads per CTA, 2 CTA(s) per SM.
+#include <cstdio>
+#include <type_traits>
+
+#include "flo_internal.h"
+
+#define FLO_VARIANT_NT 256
+#define FLO_VARIANT_CTAS 2
+
+namespace flo {
+namespace nt256 {
+
+typedef unsigned long long u64;
+typedef long long i64;
+typedef uint32_t u32;
+typedef int32_t i32;
+
+#include "encode_v2_body.cuh"
+
+}  // namespace nt256
+
+extern const EncodeVariant g_variant_nt256 = {256, 2, nt256::encode_static_smem, nt256::variant_configure,
+                                              nt256::variant_launch, nt256::variant_occupancy};
+
+}  // namespace flo

@@ -8,12 +8,13 @@
 
 namespace flo {
 
-#ifndef FLO_NT
-#define FLO_NT 512
+// The frame-encode kernel is built in three variants (threads per CTA x CTAs per SM): 512 x 1 keeps a whole
+// 44.1/48 kHz stereo frame in shared memory; 256 x 2 and 128 x 4 run several smaller frames per SM, which
+// hides the per-frame serial sections (Levinson, look-back, barriers) of small frames behind each other.
+#ifndef FLO_CH
+#define FLO_CH 16
 #endif
-constexpr int NT = FLO_NT;            // threads per CTA of the frame-encode kernel
-constexpr int NWARP = NT / 32;
-constexpr int CH = 16;                // samples per thread chunk
+constexpr int CH = FLO_CH;            // samples per thread chunk (8 or 16)
 constexpr int RING_WORDS = 4096;      // bit-packer staging ring (16 KB)
 constexpr int MAXORD = 12;
 constexpr int NCAND = 14;             // raw, fixed 0..4, lpc 5..12
@@ -88,14 +89,20 @@ struct FinalParams {
 };
 
 // kernel launchers (flo_kernels.cu)
-size_t encode_static_smem();
+struct EncodeVariant {
+    int threads;                      // threads per CTA
+    int ctas_per_sm;                  // CTAs this variant is built to co-reside per SM (register budget)
+    size_t (*static_smem)();          // bytes of the kernel's own shared state (in front of the planes)
+    cudaError_t (*configure)(size_t dyn_smem);
+    cudaError_t (*launch)(const EncodeParams &p, int grid, size_t dyn_smem, cudaStream_t st);
+    int (*occupancy)(size_t dyn_smem);
+};
+const EncodeVariant &encode_variant(int threads);     // 512, 256 or 128
 cudaError_t launch_setup(const TrackDev *tracks, uint32_t n_tracks, uint2 *frames, uint32_t n_frames, cudaStream_t st);
-cudaError_t launch_encode(const EncodeParams &p, int grid, size_t dyn_smem, cudaStream_t st);
 cudaError_t launch_toc(const FinalParams &p, cudaStream_t st);
 cudaError_t launch_crc_segments(const FinalParams &p, cudaStream_t st);
 cudaError_t launch_headers(const FinalParams &p, cudaStream_t st);
-cudaError_t configure_encode_kernel(size_t dyn_smem);
 void upload_crc_tables();
-int debug_occupancy(size_t dyn_smem);
+
 
 }  // namespace flo

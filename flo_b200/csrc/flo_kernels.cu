@@ -1,4 +1,5 @@
-// flo_kernels.cu -- sm_100a kernels of the lossless ALPC encode path.
+// flo_kernels.cu -- setup / TOC / CRC / header kernels and the variant table of the lossless ALPC encode path
+// (the frame-encode kernel itself is encode_v2_body.cuh, built three times by flo_encode_nt*.cu).
 //
 // One persistent CTA per SM takes frames from a ticket counter (ticket order ==
 // global frame order, which makes the decoupled look-back below deadlock free),
@@ -94,8 +95,6 @@ __device__ u32 x2nmodp(u64 n, unsigned k) {
     return p;
 }
 
-#include "encode_v2_body.cuh"
-
 // ----------------------------------------------------------------------------
 // setup / finalise kernels
 // ----------------------------------------------------------------------------
@@ -108,6 +107,10 @@ __global__ void k_setup_frames(const TrackDev *tracks, u32 n_tracks, uint2 *fram
         if (tracks[mid].first_frame <= g) lo = mid; else hi = mid;
     }
     frames[g] = make_uint2(lo, g - tracks[lo].first_frame);
+}
+
+__device__ __forceinline__ void put_u32le(uint8_t *p, u32 v) {
+    p[0] = (uint8_t)v; p[1] = (uint8_t)(v >> 8); p[2] = (uint8_t)(v >> 16); p[3] = (uint8_t)(v >> 24);
 }
 
 __device__ __forceinline__ u64 excl_at(const FinalParams &p, u32 g) {
@@ -231,29 +234,13 @@ __global__ void k_write_headers(const FinalParams p) {
 // ----------------------------------------------------------------------------
 // launchers
 // ----------------------------------------------------------------------------
-cudaError_t configure_encode_kernel(size_t dyn_smem) {
-    cudaError_t e;
-    if ((e = cudaFuncSetAttribute(k_encode_frames<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn_smem))) return e;
-    if ((e = cudaFuncSetAttribute(k_encode_frames<6>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn_smem))) return e;
-    if ((e = cudaFuncSetAttribute(k_encode_frames<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn_smem))) return e;
-    if ((e = cudaFuncSetAttribute(k_encode_frames<10>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn_smem))) return e;
-    return cudaFuncSetAttribute(k_encode_frames<12>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn_smem);
+extern const EncodeVariant g_variant_nt512, g_variant_nt256, g_variant_nt128;
+const EncodeVariant &encode_variant(int threads) {
+    return threads == 128 ? g_variant_nt128 : (threads == 256 ? g_variant_nt256 : g_variant_nt512);
 }
 cudaError_t launch_setup(const TrackDev *tracks, uint32_t n_tracks, uint2 *frames, uint32_t n_frames, cudaStream_t st) {
     if (n_frames == 0) return cudaSuccess;
     k_setup_frames<<<(n_frames + 255) / 256, 256, 0, st>>>(tracks, n_tracks, frames, n_frames);
-    return cudaGetLastError();
-}
-cudaError_t launch_encode(const EncodeParams &p, int grid, size_t dyn_smem, cudaStream_t st) {
-    if (p.frame_end <= p.frame_begin) return cudaSuccess;
-    // one instantiation per LPC max order (encoder.rs:289-302); levels 0-3 never try LPC (encoder.rs:204)
-    switch (p.level) {
-        case 4: k_encode_frames<6><<<grid, NT, dyn_smem, st>>>(p); break;
-        case 5: case 6: k_encode_frames<8><<<grid, NT, dyn_smem, st>>>(p); break;
-        case 7: k_encode_frames<10><<<grid, NT, dyn_smem, st>>>(p); break;
-        case 8: case 9: k_encode_frames<12><<<grid, NT, dyn_smem, st>>>(p); break;
-        default: k_encode_frames<0><<<grid, NT, dyn_smem, st>>>(p); break;
-    }
     return cudaGetLastError();
 }
 cudaError_t launch_toc(const FinalParams &p, cudaStream_t st) {
@@ -273,15 +260,5 @@ cudaError_t launch_headers(const FinalParams &p, cudaStream_t st) {
     return cudaGetLastError();
 }
 
-
-int debug_occupancy(size_t dyn_smem) {
-    int n = -1;
-    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, k_encode_frames<8>, NT, dyn_smem);
-    cudaFuncAttributes a;
-    cudaFuncGetAttributes(&a, k_encode_frames<8>);
-    printf("occupancy(NT=%d, dyn=%zu) = %d blocks/SM; regs=%d static_smem=%zu maxdyn=%d carveout=%d\n", NT, dyn_smem, n,
-           a.numRegs, a.sharedSizeBytes, a.maxDynamicSharedSizeBytes, a.preferredShmemCarveout);
-    return n;
-}
 
 }  // namespace flo
