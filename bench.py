@@ -220,11 +220,15 @@ def main() -> int:
     def step():
         off, ln = ctx.encode_batch_device(ptrs, n_list, [SR] * len(ptrs), [CH] * len(ptrs), [16] * len(ptrs),
                                           d_out.data_ptr(), bound, level=level)
-        if world > 1:       # per-track byte lengths for the final concatenation (the only exchange)
-            shard.exchange_lengths([int(v) for v in ln], ranges, rank)
+        if world > 1:       # per-track byte lengths for the final concatenation (the only exchange), non-blocking
+            pending.append(shard.exchange_lengths_async([int(v) for v in ln], ranges))
         return off, ln
 
+    pending = []
+
     def sync_all():
+        while pending:      # the concatenation offsets of every step are complete before the clock stops
+            pending.pop().result()
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()

@@ -38,6 +38,45 @@ def partition_tracks(frame_counts: Sequence[int], world: int) -> List[Tuple[int,
     return out
 
 
+class LengthExchange:
+    """Handle of an asynchronous exchange_lengths_async(); result() blocks and returns (all_lens, offsets)."""
+
+    def __init__(self, work, gathered, ranges):
+        self._work, self._gathered, self._ranges = work, gathered, ranges
+
+    def result(self):
+        if self._work is not None:
+            self._work.wait()
+        world = len(self._ranges)
+        g = self._gathered.cpu().view(world, -1)
+        all_lens = []
+        for r, (s, e) in enumerate(self._ranges):
+            all_lens.extend(int(v) for v in g[r, :e - s])
+        offsets, pos = [], 0
+        for v in all_lens:
+            offsets.append(pos)
+            pos += v
+        return all_lens, offsets
+
+
+def exchange_lengths_async(local_lens: Sequence[int], ranges: Sequence[Tuple[int, int]], group=None) -> LengthExchange:
+    """Non-blocking form of exchange_lengths (needs an initialised process group): the all_gather is only
+    waited for when the concatenation offsets are needed, so it never stalls the encode stream."""
+    import torch
+    import torch.distributed as dist
+
+    world = dist.get_world_size(group)
+    width = max(1, max((e - s) for s, e in ranges))
+    dev = torch.device("cuda", torch.cuda.current_device()) if dist.get_backend(group) == "nccl" else torch.device("cpu")
+    mine = torch.zeros(width, dtype=torch.int64)
+    if len(local_lens):
+        mine[:len(local_lens)] = torch.as_tensor([int(v) for v in local_lens], dtype=torch.int64)
+    mine = mine.to(dev, non_blocking=True)
+    gathered = torch.empty(world * width, dtype=torch.int64, device=dev)
+    work = dist.all_gather_into_tensor(gathered, mine, group=group, async_op=True)
+    return LengthExchange(work, gathered, list(ranges))
+
+
 def exchange_lengths(local_lens: Sequence[int], ranges: Sequence[Tuple[int, int]], rank: int, group=None):
     """All ranks learn every track's byte length; returns (all_lens, offsets) where offsets[i] is the
     position of track i's file image in the rank-ordered concatenation.  Uses torch.distributed

@@ -76,3 +76,33 @@ def test_two_rank_gloo_length_exchange_and_concatenation():
 def test_exchange_without_process_group_is_identity():
     lens, offs = shard.exchange_lengths([5, 7, 9], [(0, 3)], 0)
     assert lens == [5, 7, 9] and offs == [0, 5, 12]
+
+
+def _worker_async(rank, world, port, q):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        ranges = [(0, 3), (3, 4)]
+        s, e = ranges[rank]
+        mine = [10 * (i + 1) + rank for i in range(s, e)]
+        h = shard.exchange_lengths_async(mine, ranges)
+        q.put((rank,) + h.result())
+    finally:
+        dist.destroy_process_group()
+
+
+def test_async_length_exchange_gloo():
+    with socket.socket() as sk:
+        sk.bind(("127.0.0.1", 0))
+        port = sk.getsockname()[1]
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_worker_async, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    got = [q.get(timeout=120) for _ in procs]
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    for rank, lens, offs in got:
+        assert lens == [10, 20, 30, 41] and offs == [0, 10, 30, 60]
