@@ -43,6 +43,8 @@ struct ChanState {
     i32 ex_cand;                      // candidate being evaluated this round (-1 none)
     u64 ex_s;
     u32 ex_max;
+    u32 ex_fixed;                     // bit o set: fixed order o is evaluated this round (all open fixed ones at once)
+    u64 ex_s5[5];
 };
 
 struct Smem {
@@ -553,14 +555,29 @@ template <int P>
 __device__ void pass3(Smem &s, int nch) {
     u64 S;
     u32 mx;
+    u32 S5[5];                         // 32-bit partial sums: (w >> j) < 2^21 per sample, flushed every 64 chunks
     const int lane = threadIdx.x & 31;
     for_chunks(
-        s, nch, [&]() { S = 0; mx = 0; },
+        s, nch, [&]() { S = 0; mx = 0; S5[0] = S5[1] = S5[2] = S5[3] = S5[4] = 0; },
         [&](int c, int chunk) {
             const ChanState &cs = s.cs[c];
             const int cand = cs.ex_cand;
             if (cand < 0) return;
             const int i0 = chunk * CH;
+            if (cs.ex_fixed) {
+                // all open fixed candidates share one difference chain (lpc.rs:301-359); S_o for unevaluated
+                // orders is computed too and simply not used
+                const int j0 = max(cs.cand_k[1] - 1, 0), j1 = max(cs.cand_k[2] - 1, 0), j2 = max(cs.cand_k[3] - 1, 0),
+                          j3 = max(cs.cand_k[4] - 1, 0), j4 = max(cs.cand_k[5] - 1, 0);
+                i32 xf[4 + CH];
+                load_x<4>(cs, i0, xf);
+                fixed_chunk(xf, i0 == 0, [&](int j, i32 r0, i32 r1, i32 r2, i32 r3, i32 r4) {
+                    S5[0] += ((u32)abs(r0) + (u32)(r0 >> 31)) >> j0; S5[1] += ((u32)abs(r1) + (u32)(r1 >> 31)) >> j1;
+                    S5[2] += ((u32)abs(r2) + (u32)(r2 >> 31)) >> j2; S5[3] += ((u32)abs(r3) + (u32)(r3 >> 31)) >> j3;
+                    S5[4] += ((u32)abs(r4) + (u32)(r4 >> 31)) >> j4;
+                });
+                return;
+            }
             const int k = cs.cand_k[cand];
             const int jj = k >= 1 ? k - 1 : 0;
             u64 acc = 0;
@@ -592,6 +609,14 @@ __device__ void pass3(Smem &s, int nch) {
             const ChanState &cs = s.cs[c];
             const int cand = cs.ex_cand;
             if (cand < 0) return;
+            if (cs.ex_fixed) {
+#pragma unroll
+                for (int o = 0; o < 5; o++) {
+                    const i32 r = fixed_residual_at(cs, o, i);
+                    S5[o] += ((u32)abs(r) + (u32)(r >> 31)) >> max(cs.cand_k[1 + o] - 1, 0);
+                }
+                return;
+            }
             const int k = cs.cand_k[cand];
             const int jj = k >= 1 ? k - 1 : 0;
             const int mode = cand - 1;
@@ -605,6 +630,13 @@ __device__ void pass3(Smem &s, int nch) {
             const u64 t = warp_sum64(S);
             const u32 m = __reduce_max_sync(0xffffffffu, mx);
             if (lane == 0 && cs.ex_cand >= 0) { atomic_add64(&cs.ex_s, t); atomicMax(&cs.ex_max, m); }
+            if (cs.ex_fixed) {
+#pragma unroll
+                for (int o = 0; o < 5; o++) {
+                    const u64 t5 = warp_sum64((u64)S5[o]);
+                    if (lane == 0) atomic_add64(&cs.ex_s5[o], t5);
+                }
+            }
         });
 }
 
@@ -707,10 +739,16 @@ __device__ int next_open_candidate_warp(ChanState &cs, bool prune, u32 *counters
     const u64 best = warp_min64(key);
     const int pick = best == ~0ull ? -1 : (int)(best & 0xff);
     const u32 dm = __ballot_sync(0xffffffffu, dead);
+    // when a fixed predictor is due, every still-open fixed predictor of the channel is evaluated in the same round
+    u32 fm = (pick >= 1 && pick <= 5) ? ((__ballot_sync(0xffffffffu, state == CS_BOUNDED) >> 1) & 0x1fu) : 0u;
+    const u32 nfm = (u32)__popc(fm);
+    if (nfm == 1) fm = 0;                       // a single one: the one-candidate path is cheaper
     if (lane == 0) {
         if (dm) atomicAdd(counters + 5, (u32)__popc(dm));
-        if (pick >= 1 && pick <= 5) atomicAdd(counters + 4, 1u);
+        if (nfm) atomicAdd(counters + 4, nfm);
         cs.ex_cand = pick; cs.ex_s = 0; cs.ex_max = 0;
+        cs.ex_fixed = fm;
+        for (int o = 0; o < 5; o++) cs.ex_s5[o] = 0;
     }
     __syncwarp();
     return pick;
@@ -720,6 +758,14 @@ __device__ void after_pass3(ChanState &cs) {
     const int c = cs.ex_cand;
     if (c < 0) return;
     const u32 n = (u32)cs.n;
+    if (cs.ex_fixed) {
+        for (int o = 0; o < 5; o++)
+            if (cs.ex_fixed >> o & 1) {
+                cs.cand_state[1 + o] = CS_EXACT;
+                cs.cand_size[1 + o] = rice_bytes(cs.ex_s5[o], cs.cand_sumabs[1 + o], n, cs.cand_k[1 + o]);
+            }
+        return;
+    }
     if (c >= 6 && cs.ex_max > 1000000u) { cs.cand_state[c] = CS_ABSENT; return; }   // encoder.rs:269-272
     cs.cand_state[c] = CS_EXACT;
     cs.cand_size[c] = rice_bytes(cs.ex_s, cs.cand_sumabs[c], n, cs.cand_k[c]);
@@ -1249,7 +1295,7 @@ __global__ void __launch_bounds__(NT, FLO_VARIANT_CTAS) k_encode_frames(const En
                 for (int o = 0; o < 5; o++) { cs.fix_sum[o] = 0; cs.fix_or[o] = 0; }
                 for (int l = 0; l <= MAXORD; l++) cs.ac[l] = 0;
                 for (int o = 0; o < NLPC; o++) { cs.l_sum[o] = 0; cs.l_or[o] = 0; cs.l_t0[o] = 0; cs.l_t1[o] = 0; cs.lpc_ok[o] = 0; }
-                cs.ex_cand = -1; cs.ex_s = 0; cs.ex_max = 0;
+                cs.ex_cand = -1; cs.ex_s = 0; cs.ex_max = 0; cs.ex_fixed = 0;
             }
             __syncthreads();
             const long long ta0 = clock64();
