@@ -345,3 +345,31 @@ def test_pipelined_host_entry_matches_oracle(fb, ctx):
     with ctx.encode_batch(specs, 5, views=True) as res:
         for a, w in zip(res.arrays, want):
             assert a.tobytes() == w
+
+
+def test_concurrent_callers_one_context_and_two_contexts(fb):
+    """Encoder is Send + Sync in the reference (Docs/rust-api.md:374-378): calls from several threads on one
+    context serialise inside the library, separate contexts run independently; every result stays exact."""
+    import threading
+    sr = 8000
+    inputs = [pcm16_to_f32(synth_pcm16(2 * sr + 11 * i, 1 + i % 2, sr, seed=900 + i)) for i in range(6)]
+    want = [oracle.encode(x, sr, 1 + i % 2, 16, 5, b"c%d" % i) for i, x in enumerate(inputs)]
+    ctx_a, ctx_b = fb.Context(0), fb.Context(0)
+    errors = []
+
+    def worker(i, ctx):
+        try:
+            enc = fb.Encoder(sr, 1 + i % 2, 16, context=ctx)
+            for _ in range(5):
+                if enc.encode(inputs[i], b"c%d" % i) != want[i]:
+                    errors.append(i)
+        except Exception as e:                      # noqa: BLE001
+            errors.append((i, repr(e)))
+
+    threads = [threading.Thread(target=worker, args=(i, ctx_a if i < 4 else ctx_b)) for i in range(6)]
+    for t in threads:
+        t.start()
+    for t in threads:
+        t.join()
+    ctx_a.close(); ctx_b.close()
+    assert not errors, errors
