@@ -233,34 +233,43 @@ __device__ __forceinline__ void unpack8(const int4 v, i32 *t) {
     t[4] = (i32)(int16_t)(v.z & 0xffff); t[5] = v.z >> 16;
     t[6] = (i32)(int16_t)(v.w & 0xffff); t[7] = v.w >> 16;
 }
-template <int NH>
+// 16-bit pair -> two i32 through the integer dot-product unit (off the ALU pipe): dp2a_lo(w, b, c) =
+// c + w.lo * b.byte0 + w.hi * b.byte1, so b = 0x0001 picks the low half, 0x0100 the high half and
+// 0x00ff / 0xff00 subtract them.  MODE 0: plain, 1: accumulate (+), 2: accumulate (-).
+template <int MODE>
+__device__ __forceinline__ void unpack8_dp(const int4 v, i32 *t) {
+    const int w[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+    for (int i = 0; i < 4; i++) {
+        if (MODE == 0) { t[2 * i] = __dp2a_lo(w[i], 0x0001, 0); t[2 * i + 1] = __dp2a_lo(w[i], 0x0100, 0); }
+        if (MODE == 1) { t[2 * i] = __dp2a_lo(w[i], 0x0001, t[2 * i]); t[2 * i + 1] = __dp2a_lo(w[i], 0x0100, t[2 * i + 1]); }
+        if (MODE == 2) { t[2 * i] = __dp2a_lo(w[i], 0x00ff, t[2 * i]); t[2 * i + 1] = __dp2a_lo(w[i], 0xff00, t[2 * i + 1]); }
+    }
+}
+template <int NH, int MODE>
 __device__ __forceinline__ void load_plane(const int16_t *pl, int i0, i32 (&x)[NH + CH]) {
     static_assert(CH == 8 || CH == 16, "chunk of 8 or 16 samples");
-    i32 t[16 + CH];                                    // [0,16): up to 16 samples of history, [16, 16+CH): the chunk
+    // x[NH - h .. NH): history, x[NH .. NH + CH): the chunk; 8-sample pieces that reach before the frame are zero
     const int4 *p = reinterpret_cast<const int4 *>(pl + i0);
     const int4 z = make_int4(0, 0, 0, 0);
-    unpack8(p[0], t + 16);
-    if (CH == 16) unpack8(p[1], t + 24);
-    if (NH > 8) unpack8(i0 >= 16 ? p[-2] : z, t);
-    if (NH > 0) unpack8(i0 >= 8 ? p[-1] : z, t + 8);
+    i32 t[16 + CH];
+    if (MODE != 0) {
+#pragma unroll
+        for (int i = 0; i < 16 + CH; i++) t[i] = (i >= 16 - NH) ? x[i - (16 - NH)] : 0;
+    }
+    unpack8_dp<MODE>(p[0], t + 16);
+    if (CH == 16) unpack8_dp<MODE>(p[1], t + 24);
+    if (NH > 8) unpack8_dp<MODE>(i0 >= 16 ? p[-2] : z, t);
+    if (NH > 0) unpack8_dp<MODE>(i0 >= 8 ? p[-1] : z, t + 8);
 #pragma unroll
     for (int i = 0; i < NH + CH; i++) x[i] = t[16 - NH + i];
 }
 template <int NH>
 __device__ __forceinline__ void load_x(const ChanState &cs, int i0, i32 (&x)[NH + CH]) {
-    load_plane<NH>(cs.pa, i0, x);
-    const int msmode = cs.msmode;
-    if (msmode) {
-        i32 y[NH + CH];
-        load_plane<NH>(cs.pb, i0, y);
-        if (msmode == 1) {
-#pragma unroll
-            for (int i = 0; i < NH + CH; i++) x[i] = x[i] + y[i];
-        } else {
-#pragma unroll
-            for (int i = 0; i < NH + CH; i++) x[i] = x[i] - y[i];
-        }
-    }
+    load_plane<NH, 0>(cs.pa, i0, x);
+    const int msmode = cs.msmode;                      // mid = L + R, side = L - R (encoder.rs:156-170)
+    if (msmode == 1) load_plane<NH, 1>(cs.pb, i0, x);
+    else if (msmode == 2) load_plane<NH, 2>(cs.pb, i0, x);
 }
 
 // compile-time loop over LPC orders
