@@ -14,3 +14,5 @@ for lv in (0,2,5,9):
     for _ in range(3): ctx.encode_batch_device([x.data_ptr()],n,[SR],[CH],[16],out.data_ptr(),bound,level=lv)
     t=ctx.last_timing(); c=ctx.last_counters()["phase_clocks"]; f=secs
     print(f"level {lv}: kernel {t['encode_ms']:.3f} ms; per-frame clocks: " + ", ".join(f"{k} {v/f:.0f}" for k,v in c.items()))
+t = ctx.last_timing()
+print("last call timing (ms):", {k: round(v, 3) if isinstance(v, float) else v for k, v in t.items()})
