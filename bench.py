@@ -272,7 +272,7 @@ def main() -> int:
                 "traffic": traffic, "kernel": "k_encode_frames", "kernel_ms": k_ms, "peak_source": peak_src,
                 "algorithmic_bytes_per_launch": alg_bytes,
                 "note": "issue/ALU-pipe bound at level 5 (10 exhaustive candidates per channel: ~200 thread-instructions per "
-                        "channel-sample); DRAM traffic is 1.08 x the algorithmic bytes (some write-back of the L2-resident "
+                        "channel-sample); DRAM traffic is 1.07 x the algorithmic bytes (some write-back of the L2-resident "
                         "16-bit planes, no re-reads of the input); see DESIGN.md section 6"}
 
     # side measurements (not the headline): other compression levels and the PCM16 entry, same stream
