@@ -373,3 +373,40 @@ def test_concurrent_callers_one_context_and_two_contexts(fb):
         t.join()
     ctx_a.close(); ctx_b.close()
     assert not errors, errors
+
+
+def test_seeded_random_sweep(fb, ctx):
+    """48 seeded random cases: channels, rates, lengths (incl. ragged), levels, amplitudes (full-scale stereo makes
+    17-bit mid/side values), signal mixes with silent and noisy stretches, both entries, batched in groups."""
+    rng = np.random.default_rng(0xF17)
+    specs, want, fmts = [], [], []
+    for i in range(48):
+        ch = int(rng.integers(1, 5))
+        sr = int(rng.choice([1000, 2205, 4000, 8000, 11025, 12000]))
+        n = int(rng.integers(0, 3 * sr + 1))
+        kind = str(rng.choice(["multitone", "speech", "tone", "sweep"]))
+        pcm = synth_pcm16(n, ch, sr, seed=1000 + i, kind=kind, noise_lsb=int(rng.choice([1, 8, 64, 512]))).astype(np.int32)
+        if rng.random() < 0.4:                                   # loud: drive mid = L + R beyond 16 bits
+            pcm = np.clip(pcm * 6, -32768, 32767)
+        if rng.random() < 0.3 and n > 20:                        # a silent stretch and a white-noise stretch
+            a, b = sorted(rng.integers(0, n, 2))
+            pcm.reshape(-1, ch)[a:b] = 0
+            c0 = int(rng.integers(0, n))
+            pcm.reshape(-1, ch)[c0:c0 + n // 7] = rng.integers(-30000, 30000, pcm.reshape(-1, ch)[c0:c0 + n // 7].shape)
+        pcm = pcm.astype(np.int16)
+        ragged = int(rng.integers(0, ch)) if ch > 1 else 0
+        pcm = pcm[:len(pcm) - ragged] if ragged and len(pcm) > ragged else pcm
+        level = int(rng.integers(0, 10))
+        meta = bytes(rng.integers(0, 256, int(rng.integers(0, 40)), dtype=np.uint8))
+        if i % 2:
+            out = fb.Encoder(sr, ch, 16, context=ctx).with_compression(level).encode_pcm16(pcm, meta)
+            check_same(out, oracle.encode_pcm16(pcm, sr, ch, 16, level, meta), f"case {i} pcm16 ch={ch} sr={sr} n={n} L{level}")
+        else:
+            x = pcm16_to_f32(pcm)
+            out = fb.Encoder(sr, ch, 24, context=ctx).with_compression(level).encode(x, meta)
+            check_same(out, oracle.encode(x, sr, ch, 24, level, meta), f"case {i} f32 ch={ch} sr={sr} n={n} L{level}")
+        if level == 5:
+            specs.append(fb.TrackSpec(pcm, sr, ch, 16, meta)); want.append(oracle.encode_pcm16(pcm, sr, ch, 16, 5, meta))
+    got = ctx.encode_batch(specs, 5, fb.FMT_PCM16)
+    for i, (g, w) in enumerate(zip(got, want)):
+        check_same(g, w, f"batched level-5 case {i}")
