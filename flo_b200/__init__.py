@@ -4,6 +4,7 @@ Drop-in for `libflo_audio::Encoder::{new, with_compression, encode}` only; see D
 """
 from ._lib import FMT_F32, FMT_PCM16, FloError, SO_PATH
 from .encoder import Context, Encoder, TrackSpec, default_context, encode_batch
+from . import reflo
 
 __all__ = ["Encoder", "Context", "TrackSpec", "encode_batch", "default_context", "FloError", "FMT_F32", "FMT_PCM16",
-           "SO_PATH"]
+           "SO_PATH", "reflo"]
