@@ -3,8 +3,8 @@
 Drop-in for `libflo_audio::Encoder::{new, with_compression, encode}` only; see DESIGN.md.
 """
 from ._lib import FMT_F32, FMT_PCM16, FloError, SO_PATH
-from .encoder import Context, Encoder, TrackSpec, default_context, encode_batch
+from .encoder import Context, Decoder, Encoder, TrackSpec, default_context, encode_batch
 from . import reflo
 
-__all__ = ["Encoder", "Context", "TrackSpec", "encode_batch", "default_context", "FloError", "FMT_F32", "FMT_PCM16",
+__all__ = ["Encoder", "Decoder", "Context", "TrackSpec", "encode_batch", "default_context", "FloError", "FMT_F32", "FMT_PCM16",
            "SO_PATH", "reflo"]

@@ -25,6 +25,13 @@ class Out(C.Structure):
     _fields_ = [("data", C.c_void_p), ("len", C.c_size_t)]
 
 
+class Info(C.Structure):
+    """flo_info: header fields of a decoded file."""
+    _fields_ = [("sample_rate", C.c_uint32), ("channels", C.c_uint8), ("bit_depth", C.c_uint8), ("level", C.c_uint8),
+                ("version_major", C.c_uint8), ("total_samples", C.c_uint64), ("decoded_frames", C.c_uint64),
+                ("n_frames", C.c_uint32), ("data_crc32", C.c_uint32), ("meta_offset", C.c_uint64), ("meta_size", C.c_uint64)]
+
+
 class CandReport(C.Structure):
     _fields_ = [("k", C.c_int32), ("pad", C.c_int32), ("size", C.c_int64)]
 
@@ -34,7 +41,7 @@ EXPORTS = [
     "flo_ctx_create", "flo_ctx_destroy", "flo_encode", "flo_encode_pcm16", "flo_encode_batch",
     "flo_encode_batch_device", "flo_output_bound", "flo_ctx_set_stream", "flo_ctx_last_timing",
     "flo_ctx_last_counters", "flo_ctx_enable_report", "flo_ctx_read_report", "flo_host_alloc", "flo_host_free", "flo_free",
-    "flo_last_error", "flo_version", "flo_device_count",
+    "flo_last_error", "flo_version", "flo_device_count", "flo_decode", "flo_decode_device",
 ]
 
 _lib = None
@@ -74,6 +81,10 @@ def lib() -> C.CDLL:
     L.flo_ctx_enable_report.argtypes = [vp, C.c_int]
     L.flo_ctx_read_report.restype = C.c_int
     L.flo_ctx_read_report.argtypes = [vp, u32, u32, C.POINTER(CandReport)]
+    L.flo_decode.restype = C.c_int
+    L.flo_decode.argtypes = [vp, vp, sz, C.POINTER(vp), C.POINTER(sz), C.POINTER(Info)]
+    L.flo_decode_device.restype = C.c_int
+    L.flo_decode_device.argtypes = [vp, vp, sz, vp, sz, C.POINTER(sz), C.POINTER(Info)]
     L.flo_host_alloc.restype = vp
     L.flo_host_alloc.argtypes = [sz]
     L.flo_host_free.restype = None

@@ -166,6 +166,7 @@ struct flo_ctx {
     cudaEvent_t ev[8] = {};
     cudaEvent_t ev_in[MAX_WAVES] = {}, ev_k[MAX_WAVES] = {}, ev_fin = nullptr;
     DevBuf in, out, meta, tracks, frames, ctrl, fexcl, fsize, foff, plane, cres, report;
+    DevBuf dec_frames, dec_units, dec_base, dec_ctl;      // decoder scratch
     uint64_t counters[24] = {0};      // [0..7] analysis counters, [8..23] per-phase SM clock sums
     HostBuf h_small, h_out;
     bool report_on = false;
@@ -225,7 +226,7 @@ extern "C" void flo_ctx_destroy(flo_ctx *c) {
     cudaDeviceSynchronize();
     if (c->l2_win_ptr) { cudaCtxResetPersistingL2Cache(); cudaGetLastError(); }
     for (DevBuf *b : {&c->in, &c->out, &c->meta, &c->tracks, &c->frames, &c->ctrl, &c->fexcl, &c->fsize,
-                      &c->foff, &c->plane, &c->cres, &c->report})
+                      &c->foff, &c->plane, &c->cres, &c->report, &c->dec_frames, &c->dec_units, &c->dec_base, &c->dec_ctl})
         b->release();
     c->h_small.release();
     c->h_out.release();
@@ -723,4 +724,181 @@ extern "C" int flo_encode(flo_ctx *c, const float *samples, size_t n, uint32_t s
 extern "C" int flo_encode_pcm16(flo_ctx *c, const int16_t *pcm, size_t n, uint32_t sr, uint8_t ch, uint8_t bits,
                                 uint8_t level, const uint8_t *meta, size_t meta_len, uint8_t **out, size_t *out_len) {
     return encode_one(c, pcm, n, FLO_FMT_PCM16, sr, ch, bits, level, meta, meta_len, out, out_len);
+}
+
+// ------------------------------------------------------------------------------------------------
+// Lossless decoder (include/flo_b200.h: flo_decode / flo_decode_device)
+// ------------------------------------------------------------------------------------------------
+namespace {
+
+struct FileHead {
+    uint8_t vmaj, channels, bits, level;
+    uint32_t sample_rate, crc, n_toc;
+    uint64_t total, toc_size, data_size, extra_size, meta_size;
+    uint64_t toc_pos, data_start, data_end, meta_off;
+    bool tail_eof;
+};
+inline uint64_t le(const uint8_t *p, int n) { uint64_t v = 0; for (int i = 0; i < n; i++) v |= (uint64_t)p[i] << (8 * i); return v; }
+
+// Reader::read up to the DATA chunk (reader.rs:16-99), on the first min(len, 74) bytes of the file.
+int parse_head(const uint8_t *h, size_t len, FileHead &H) {
+    if (len < 4 || memcmp(h, "FLO!", 4) != 0) { set_err("Invalid flo file: bad magic"); return FLO_ERR_ARG; }
+    if (len < 70) { set_err("Unexpected end of file"); return FLO_ERR_ARG; }
+    H.vmaj = h[4]; H.sample_rate = (uint32_t)le(h + 8, 4); H.channels = h[12]; H.bits = h[13];
+    H.total = le(h + 14, 8); H.level = h[22]; H.crc = (uint32_t)le(h + 26, 4);
+    H.toc_size = le(h + 38, 8); H.data_size = le(h + 46, 8); H.extra_size = le(h + 54, 8); H.meta_size = le(h + 62, 8);
+    H.n_toc = 0; H.toc_pos = 70; H.data_start = 70;
+    if (H.toc_size >= 4) {
+        if (len < 74) { set_err("Unexpected end of file"); return FLO_ERR_ARG; }
+        H.n_toc = (uint32_t)le(h + 70, 4);
+        if (H.n_toc > 100000) { set_err("Invalid TOC: too many entries"); return FLO_ERR_ARG; }
+        H.toc_pos = 74;
+        H.data_start = 74 + 20ull * H.n_toc;
+        if (H.data_start > len) { set_err("Unexpected end of file"); return FLO_ERR_ARG; }
+    }
+    H.data_end = H.data_start + H.data_size;
+    if (H.data_end < H.data_start) { set_err("Unexpected end of file"); return FLO_ERR_ARG; }
+    // after the frames: pos = data_end; skip(extra) clamps to the file; read_bytes(meta_size) (reader.rs:39-43)
+    uint64_t pos = H.data_end + H.extra_size;
+    if (pos < H.data_end || pos > len) pos = len;
+    H.meta_off = pos;
+    H.tail_eof = H.meta_size > len - pos;
+    return FLO_OK;
+}
+
+int decode_error(uint32_t key) {
+    const uint32_t kind = key & 15u, frame = key >> 13;
+    switch (kind) {
+    case flo::DEC_TOO_MANY: set_err("Invalid frame: too many samples"); break;
+    case flo::DEC_BAD_ORDER: set_err("Invalid LPC order"); break;
+    case flo::DEC_EOF: set_err("Unexpected end of file"); break;
+    case flo::DEC_TRANSFORM: set_err("frame %u is a transform (lossy) frame: not supported by the lossless GPU decoder", frame); break;
+    default: set_err("frame %u: unsupported Rice parameter (> 31)", frame); break;
+    }
+    return FLO_ERR_ARG;
+}
+
+int decode_impl(flo_ctx *c, const uint8_t *h_file, const void *d_file, size_t len, float *d_out_user, size_t cap,
+                float **out, size_t *n_out, flo_info *info) {
+    if (!c || !n_out || (!h_file && !d_file) || (h_file && !out)) { set_err("bad argument"); return FLO_ERR_ARG; }
+    *n_out = 0;
+    if (out) *out = nullptr;
+    std::lock_guard<std::mutex> lk(c->mu);
+    CK(cudaSetDevice(c->device));
+    cudaStream_t st = c->stream;
+    uint8_t head[80] = {0};
+    const size_t have = len < 74 ? len : 74;
+    if (h_file) memcpy(head, h_file, have);
+    else if (have) { CK(cudaMemcpyAsync(head, d_file, have, cudaMemcpyDeviceToHost, st)); CK(cudaStreamSynchronize(st)); }
+    FileHead H;
+    if (int rc = parse_head(head, len, H)) return rc;
+    const uint32_t C = H.channels;
+
+    const uint8_t *df = (const uint8_t *)d_file;
+    CK(cudaEventRecord(c->ev[0], st));
+    if (h_file) {
+        if (int rc = c->in.reserve(len + 64)) return rc;
+        CK(cudaMemcpyAsync(c->in.p, h_file, len, cudaMemcpyHostToDevice, st));
+        df = (const uint8_t *)c->in.p;
+    }
+    CK(cudaEventRecord(c->ev[1], st));
+    const size_t nf = H.n_toc ? H.n_toc : 1;
+    if (int rc = c->dec_frames.reserve(nf * sizeof(flo::DecFrame))) return rc;
+    if (int rc = c->dec_units.reserve(nf * (C ? C : 1) * sizeof(flo::DecUnit))) return rc;
+    if (int rc = c->dec_base.reserve(nf * sizeof(uint64_t))) return rc;
+    if (int rc = c->dec_ctl.reserve(64)) return rc;
+    if (int rc = c->h_small.reserve(256)) return rc;
+    uint32_t *hc = (uint32_t *)c->h_small.p;
+    hc[0] = H.n_toc; hc[1] = 0xFFFFFFFFu; hc[2] = 0; hc[3] = 0;
+    CK(cudaMemcpyAsync(c->dec_ctl.p, hc, 16, cudaMemcpyHostToDevice, st));
+
+    flo::DecodeParams p;
+    p.file = df; p.len = len; p.toc_pos = H.toc_pos; p.n_toc = H.n_toc; p.channels = C;
+    p.data_start = H.data_start; p.data_end = H.data_end;
+    p.frames = (flo::DecFrame *)c->dec_frames.p; p.units = (flo::DecUnit *)c->dec_units.p;
+    p.base = (unsigned long long *)c->dec_base.p; p.ctl = (uint32_t *)c->dec_ctl.p; p.out = nullptr;
+    CK(flo::launch_decode_parse(p, st));
+    CK(cudaEventRecord(c->ev[2], st));
+    CK(cudaMemcpyAsync(hc + 8, c->dec_ctl.p, 16, cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    const uint32_t keep = hc[8] < H.n_toc ? hc[8] : H.n_toc;
+    if (hc[9] != 0xFFFFFFFFu && (hc[9] >> 13) < keep) return decode_error(hc[9]);
+    const uint64_t total = (uint64_t)hc[10] | ((uint64_t)hc[11] << 32);
+    const uint64_t n = total * C;
+    *n_out = (size_t)n;
+
+    float *d_out = d_out_user;
+    if (h_file) {
+        if (int rc = c->out.reserve(n * sizeof(float) + 64)) return rc;
+        d_out = (float *)c->out.p;
+    } else if (n > cap || (n && !d_out_user)) {
+        set_err("flo_decode_device: output capacity %zu floats, %llu needed", cap, (unsigned long long)n);
+        return FLO_ERR_ARG;
+    }
+    p.out = d_out;
+    p.n_toc = keep;
+    CK(cudaEventRecord(c->ev[3], st));
+    uint32_t launches = H.n_toc ? 2 : 1;
+    if (n) { CK(flo::launch_decode_units(p, st)); launches++; }
+    CK(cudaEventRecord(c->ev[4], st));
+    CK(cudaMemcpyAsync(hc + 8, c->dec_ctl.p, 16, cudaMemcpyDeviceToHost, st));
+
+    OutBlock *blk = nullptr;
+    float *h_out = nullptr;
+    if (h_file) {
+        const size_t bytes = (size_t)n * sizeof(float);
+        if (bytes >= SMALL_OUTPUT) {
+            blk = take_block(bytes);
+            if (!blk) { set_err("pinned output allocation (%zu bytes) failed", bytes); return FLO_ERR_NOMEM; }
+            h_out = (float *)blk->base;
+        } else {
+            h_out = (float *)malloc(bytes ? bytes : 1);
+            if (!h_out) { set_err("malloc(%zu) failed", bytes); return FLO_ERR_NOMEM; }
+        }
+        if (bytes) {
+            cudaError_t e = cudaMemcpyAsync(h_out, d_out, bytes, cudaMemcpyDeviceToHost, st);
+            if (e != cudaSuccess) { if (blk) drop_block(blk); else free(h_out); CK(e); }
+        }
+    }
+    cudaEventRecord(c->ev[5], st);
+    cudaError_t e = cudaStreamSynchronize(st);
+    int rc = FLO_OK;
+    if (e != cudaSuccess) { set_err("CUDA error %s in decode: %s", cudaGetErrorName(e), cudaGetErrorString(e)); rc = FLO_ERR_CUDA; }
+    else if (hc[9] != 0xFFFFFFFFu && (hc[9] >> 13) < keep) rc = decode_error(hc[9]);
+    else if (H.tail_eof) { set_err("Unexpected end of file"); rc = FLO_ERR_ARG; }
+    if (rc) {
+        if (blk) drop_block(blk); else free(h_out);
+        *n_out = 0;
+        return rc;
+    }
+    if (h_file) {
+        if (blk) publish_block(blk, 1);
+        *out = h_out;
+    }
+    float t = 0;
+    for (float &m : c->ms) m = 0;
+    if (cudaEventElapsedTime(&t, c->ev[1], c->ev[4]) == cudaSuccess) c->ms[0] = t;
+    if (cudaEventElapsedTime(&t, c->ev[3], c->ev[4]) == cudaSuccess) c->ms[1] = t;
+    if (cudaEventElapsedTime(&t, c->ev[1], c->ev[2]) == cudaSuccess) c->ms[3] = t;
+    if (cudaEventElapsedTime(&t, c->ev[0], c->ev[1]) == cudaSuccess) c->ms[4] = t;
+    if (cudaEventElapsedTime(&t, c->ev[4], c->ev[5]) == cudaSuccess) c->ms[5] = t;
+    c->launches = launches;
+    if (info) {
+        info->sample_rate = H.sample_rate; info->channels = H.channels; info->bit_depth = H.bits; info->level = H.level;
+        info->version_major = H.vmaj; info->total_samples = H.total; info->decoded_frames = total; info->n_frames = keep;
+        info->data_crc32 = H.crc; info->meta_offset = H.meta_off; info->meta_size = H.meta_size;
+    }
+    return FLO_OK;
+}
+
+}  // namespace
+
+extern "C" int flo_decode(flo_ctx *c, const uint8_t *file, size_t len, float **out, size_t *n_interleaved, flo_info *info) {
+    if (!file) { set_err("bad argument"); return FLO_ERR_ARG; }
+    return decode_impl(c, file, nullptr, len, nullptr, 0, out, n_interleaved, info);
+}
+extern "C" int flo_decode_device(flo_ctx *c, const void *d_file, size_t len, float *d_out, size_t d_out_capacity,
+                                 size_t *n_interleaved, flo_info *info) {
+    if (!d_file) { set_err("bad argument"); return FLO_ERR_ARG; }
+    return decode_impl(c, nullptr, d_file, len, d_out, d_out_capacity, nullptr, n_interleaved, info);
 }

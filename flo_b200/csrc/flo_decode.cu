@@ -1,0 +1,364 @@
+// flo_decode.cu -- lossless decoder kernels.
+//
+// Restates, for the GPU, what Reader::read (libflo/src/reader.rs:16-247) and Decoder::decode_file
+// (libflo/src/lossless/decoder.rs:21-273) do on the CPU.  Rice decoding (core/rice.rs:123-159) and LPC synthesis
+// (decoder.rs:152-184) are serial per channel, so the unit of parallel work is one channel of one frame:
+// one lane per unit, 32 units per warp, all lanes stepping sample by sample in lock step.  That makes the two
+// channels of a stereo frame neighbours in a warp, so the mid/side inverse is one shuffle and every lane writes
+// its own channel of the interleaved f32 output directly -- no intermediate planes.
+#include "flo_internal.h"
+
+namespace flo {
+namespace {
+
+constexpr uint32_t FULL = 0xFFFFFFFFu;
+constexpr uint8_t FT_TRANSFORM = 253, FT_RAW = 254;
+
+__device__ __forceinline__ uint32_t rd32(const uint8_t *p) {
+    return (uint32_t)p[0] | ((uint32_t)p[1] << 8) | ((uint32_t)p[2] << 16) | ((uint32_t)p[3] << 24);
+}
+__device__ __forceinline__ unsigned long long rd64(const uint8_t *p) { return (unsigned long long)rd32(p) | ((unsigned long long)rd32(p + 4) << 32); }
+__device__ __forceinline__ void dec_fail(uint32_t *ctl, uint32_t frame, uint32_t chan1, uint32_t kind) {
+    atomicMin(&ctl[1], (frame << 13) | (chan1 << 4) | kind);
+}
+
+// One thread per TOC entry: read_data_chunk / read_frame (reader.rs:101-166) up to the channel payloads.
+__global__ void k_dec_parse(DecodeParams p) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= p.n_toc) return;
+    const uint8_t *f = p.file;
+    const unsigned long long off = rd64(f + p.toc_pos + 20ull * i + 4);
+    const unsigned long long fstart = p.data_start + off;
+    DecFrame fr = {0u, 0u};
+    if (fstart < p.data_start || fstart >= p.data_end) {          // reader.rs:116-118: stop at the first such entry
+        atomicMin(&p.ctl[0], i);
+        p.frames[i] = fr;
+        return;
+    }
+    if (fstart + 6 > p.len) { dec_fail(p.ctl, i, 0, DEC_EOF); p.frames[i] = fr; return; }
+    const uint32_t type = f[fstart], n = rd32(f + fstart + 1), flags = f[fstart + 5];
+    fr.type_flags = type | (flags << 8);
+    fr.n = n;
+    p.frames[i] = fr;
+    if (type == FT_TRANSFORM) { dec_fail(p.ctl, i, 0, DEC_TRANSFORM); return; }
+    unsigned long long pos = fstart + 6;
+    for (uint32_t c = 0; c < p.channels; c++) {
+        DecUnit u = {0ull, 0u, 0u};
+        if (pos + 4 > p.len) { dec_fail(p.ctl, i, c + 1, DEC_EOF); break; }
+        const uint32_t ch_size = rd32(f + pos);
+        const unsigned long long payload = pos + 4, ch_end = payload + ch_size;
+        if (n > 2000000u) { dec_fail(p.ctl, i, c + 1, DEC_TOO_MANY); break; }       // reader.rs:175-177
+        if (type >= 1 && type <= 12) {
+            if (ch_end > p.len) { dec_fail(p.ctl, i, c + 1, DEC_EOF); break; }       // header or residual read runs off the file
+        } else if (type == FT_RAW) {
+            const unsigned long long need = 2ull * n;
+            if (payload + (need < ch_size ? need : ch_size) > p.len) { dec_fail(p.ctl, i, c + 1, DEC_EOF); break; }
+        }
+        u.pos = payload; u.size = ch_size;
+        p.units[(size_t)i * p.channels + c] = u;
+        pos = ch_end;
+    }
+}
+
+// Exclusive scan of frame_samples over the frames the reader keeps (one CTA; at most 100000 entries, reader.rs:86).
+__global__ void __launch_bounds__(1024) k_dec_scan(DecodeParams p) {
+    __shared__ unsigned long long wtot[32];
+    __shared__ unsigned long long s_carry;
+    const uint32_t tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
+    const uint32_t keep = p.ctl[0] < p.n_toc ? p.ctl[0] : p.n_toc;
+    if (tid == 0) s_carry = 0;
+    __syncthreads();
+    for (uint32_t b0 = 0; b0 < p.n_toc; b0 += 1024) {
+        const uint32_t i = b0 + tid;
+        unsigned long long v = 0;
+        if (i < keep) v = p.frames[i].n;
+        else if (i < p.n_toc) p.frames[i].n = 0;
+        unsigned long long inc = v;
+        #pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            unsigned long long t = __shfl_up_sync(FULL, inc, d);
+            if ((int)lane >= d) inc += t;
+        }
+        if (lane == 31) wtot[w] = inc;
+        __syncthreads();
+        unsigned long long wb = 0, tot = 0;
+        for (uint32_t k = 0; k < 32; k++) { unsigned long long t = wtot[k]; if (k < w) wb += t; tot += t; }
+        const unsigned long long carry = s_carry;
+        if (i < p.n_toc) p.base[i] = carry + wb + inc - v;
+        __syncthreads();
+        if (tid == 0) s_carry = carry + tot;
+        __syncthreads();
+    }
+    if (tid == 0) *reinterpret_cast<unsigned long long *>(p.ctl + 2) = s_carry;
+}
+
+// ---- bit reader: MSB-first (rice.rs:217-260), bits past the end of the payload read as 0 ----
+struct BitIn {
+    const uint4 *vp, *vend;
+    uint4 cur, nx1, nx2;              // 16-byte vectors in flight: the loads run two vectors ahead of the bits in use
+    uint32_t j, left;                 // next word of `cur`; payload bytes not yet popped
+    unsigned long long buf;           // MSB-aligned window
+    int nb;                           // bits in the window
+};
+__device__ __forceinline__ uint4 ldv(const uint4 *p, const uint4 *end) { return p < end ? __ldg(p) : make_uint4(0u, 0u, 0u, 0u); }
+__device__ __forceinline__ uint32_t pop_raw(BitIn &b) {
+    const uint32_t w = b.j == 0 ? b.cur.x : b.j == 1 ? b.cur.y : b.j == 2 ? b.cur.z : b.cur.w;
+    if (++b.j == 4) { b.j = 0; b.cur = b.nx1; b.nx1 = b.nx2; b.nx2 = ldv(b.vp, b.vend); b.vp++; }
+    return __byte_perm(w, 0u, 0x0123);
+}
+__device__ __forceinline__ uint32_t pop(BitIn &b) {
+    const uint32_t w = pop_raw(b);
+    const uint32_t valid = b.left < 4u ? b.left : 4u;
+    b.left -= valid;
+    return valid == 4u ? w : (w & ~(0xFFFFFFFFu >> (8u * valid)));
+}
+__device__ __forceinline__ void bits_init(BitIn &b, const uint8_t *file, unsigned long long len, unsigned long long start, uint32_t nbytes) {
+    const uintptr_t a = (uintptr_t)(file + start), a0 = a & ~(uintptr_t)15;
+    b.vend = (const uint4 *)(((uintptr_t)(file + len) + 15) & ~(uintptr_t)15);
+    b.vp = nbytes ? (const uint4 *)a0 : b.vend;
+    b.cur = ldv(b.vp, b.vend); b.vp++;
+    b.nx1 = ldv(b.vp, b.vend); b.vp++;
+    b.nx2 = ldv(b.vp, b.vend); b.vp++;
+    const uint32_t sk = (uint32_t)(a - a0), sb = sk & 3u;
+    b.j = sk >> 2;
+    b.left = nbytes; b.buf = 0; b.nb = 0;
+    if (sb) {                          // payload starts inside a word
+        uint32_t w = pop_raw(b) << (8u * sb);
+        const uint32_t room = 4u - sb, valid = b.left < room ? b.left : room;
+        b.left -= valid;
+        w &= ~(0xFFFFFFFFu >> (8u * valid));
+        b.buf = (unsigned long long)w << 32;
+        b.nb = 32 - 8 * (int)sb;
+    }
+}
+__device__ __forceinline__ void refill(BitIn &b) {
+    if (b.nb <= 32) { b.buf |= (unsigned long long)pop(b) << (32 - b.nb); b.nb += 32; }
+}
+// decode_i32's loop body (rice.rs:127-155): unary quotient (ones, capped at 256 reads), k-bit remainder, zigzag.
+// Rare path: the code does not fit the bits on hand (long unary run, large k).
+__device__ __forceinline__ uint32_t rice_slow(BitIn &b, uint32_t k) {
+    uint32_t q = 0;
+    for (;;) {
+        int run = __clzll((long long)~b.buf);
+        if (run > b.nb) run = b.nb;
+        const bool more = run == b.nb;                     // every loaded bit is a one: the run goes on
+        if (q + (uint32_t)run >= 256u) {                   // rice.rs:139-141: stops after the 256th one, no terminator read
+            const int take = (int)(256u - q);
+            b.buf = take >= 64 ? 0ull : b.buf << take; b.nb -= take; q = 256u;
+            break;
+        }
+        q += (uint32_t)run;
+        if (!more) { b.buf = (b.buf << run) << 1; b.nb -= run + 1; break; }
+        b.buf = 0; b.nb = 0;
+        refill(b);
+    }
+    refill(b);
+    uint32_t r = 0;
+    if (k) { r = (uint32_t)(b.buf >> (64 - k)); b.buf <<= k; b.nb -= (int)k; }
+    return (q << k) | r;
+}
+__device__ __forceinline__ int32_t rice_next(BitIn &b, uint32_t k) {
+    refill(b);                                             // 33..64 bits on hand; unused low bits of the window are 0
+    const int run = __clzll((long long)~b.buf);            // leading ones
+    const int used = run + 1 + (int)k;
+    uint32_t u;
+    if (__builtin_expect(used <= b.nb, 1)) {
+        const unsigned long long t = (b.buf << run) << 1;
+        u = ((uint32_t)run << k) | (uint32_t)((t >> 1) >> (63 - k));
+        b.buf = t << k; b.nb -= used;
+    } else {
+        u = rice_slow(b, k);
+    }
+    return (int32_t)(u >> 1) ^ -(int32_t)(u & 1u);
+}
+
+__constant__ int c_fixed[5][4] = {{0, 0, 0, 0}, {1, 0, 0, 0}, {2, -1, 0, 0}, {3, -3, 1, 0}, {4, -6, 4, -1}};   // decoder.rs:199-259
+
+enum { M_ZERO = 0, M_RICE = 1, M_PCM = 2 };
+
+struct Lane {
+    BitIn bits;
+    const uint8_t *pcm; uint32_t pcm_bytes;
+    float *outp; uint32_t stride;
+    uint32_t n, k;
+    int src;                          // M_*
+    int order, shift;                 // taps in use; >> shift (0 for the fixed predictors)
+    bool fixed, ms, odd;
+};
+
+__device__ __forceinline__ int32_t next_residual(Lane &L, uint32_t i) {
+    int32_t r = rice_next(L.bits, L.k);
+    if (L.src == M_PCM) {             // decoder.rs:132-143
+        r = 0;
+        if (2ull * i + 1 < L.pcm_bytes) r = (int16_t)((uint16_t)__ldg(L.pcm + 2ull * i) | ((uint16_t)__ldg(L.pcm + 2ull * i + 1) << 8));
+    }
+    return r;
+}
+// mid/side inverse (decoder.rs:75-89), i32 -> f32 (audio_constants.rs:24-26), interleaved store
+__device__ __forceinline__ void emit(const Lane &L, uint32_t i, int32_t s) {
+    const int32_t o = __shfl_xor_sync(FULL, s, 1);
+    int32_t v = s;
+    if (L.ms) {
+        const uint32_t m = (uint32_t)(L.odd ? o : s), d = (uint32_t)(L.odd ? s : o);
+        v = (int32_t)(L.odd ? m - d : m + d) / 2;
+    }
+    if (i < L.n) L.outp[(size_t)i * L.stride] = __fmul_rn(__int2float_rn(v), 1.0f / 32767.0f);
+}
+
+// Steady state for predictors of at most ORD taps: history newest-first in ORD registers.  The loop is kept
+// rolled (one sample per trip, ORD register moves) so that its body stays inside the instruction cache --
+// with one warp per scheduler nothing else hides a fetch miss.
+template <int ORD>
+__device__ __forceinline__ uint32_t synth_blocks(Lane &L, uint32_t i, uint32_t nmax, const int32_t (&c12)[12], int32_t (&hist)[12]) {
+    int32_t c[ORD], h[ORD];
+    #pragma unroll
+    for (int j = 0; j < ORD; j++) { c[j] = c12[j]; h[j] = hist[j]; }
+    const int sh = L.shift;
+    #pragma unroll 1
+    for (; i < nmax; i++) {
+        const int32_t r = next_residual(L, i);
+        long long acc = 0;
+        #pragma unroll
+        for (int j = ORD - 1; j >= 0; j--) acc += (long long)c[j] * (long long)h[j];    // newest sample last: shortest carried chain
+        const int32_t s = (int32_t)((uint32_t)(int32_t)(acc >> sh) + (uint32_t)r);
+        #pragma unroll
+        for (int j = ORD - 1; j > 0; j--) h[j] = h[j - 1];
+        h[0] = s;
+        emit(L, i, s);
+    }
+    #pragma unroll
+    for (int j = 0; j < ORD; j++) hist[j] = h[j];
+    return i;
+}
+
+// Generic step with the history newest-first in hist[]: warm-up rules (decoder.rs:163-165, 199-259) and block tails.
+__device__ __forceinline__ void synth_step(Lane &L, uint32_t i, const int32_t (&c12)[12], int32_t (&hist)[12]) {
+    const int32_t r = next_residual(L, i);
+    int32_t pred = 0;
+    if (i >= (uint32_t)L.order) {
+        long long acc = 0;
+        #pragma unroll
+        for (int j = 0; j < 12; j++) acc += (long long)c12[j] * (long long)hist[j];
+        pred = (int32_t)(acc >> L.shift);
+    } else if (L.fixed) {                                  // sample i < order uses the order-i predictor
+        long long acc = 0;
+        #pragma unroll
+        for (int j = 0; j < 4; j++) acc += (long long)c_fixed[i][j] * (long long)hist[j];
+        pred = (int32_t)acc;
+    }
+    const int32_t s = (int32_t)((uint32_t)pred + (uint32_t)r);
+    #pragma unroll
+    for (int j = 11; j > 0; j--) hist[j] = hist[j - 1];
+    hist[0] = s;
+    emit(L, i, s);
+}
+
+__global__ void __launch_bounds__(32) k_dec_units(DecodeParams p) {
+    const uint32_t lane = threadIdx.x;
+    const unsigned long long u = (unsigned long long)blockIdx.x * 32 + lane;
+    const uint32_t C = p.channels;
+    const uint32_t keep = p.ctl[0] < p.n_toc ? p.ctl[0] : p.n_toc;
+    const unsigned long long n_units = (unsigned long long)keep * C;
+    const uint8_t *f = p.file;
+
+    Lane L;
+    L.n = 0; L.k = 0; L.src = M_ZERO; L.order = 0; L.shift = 0; L.fixed = false; L.ms = false; L.odd = (lane & 1u) != 0;
+    L.pcm = f; L.pcm_bytes = 0; L.outp = p.out; L.stride = C;
+    int32_t c12[12], hist[12];
+    #pragma unroll
+    for (int j = 0; j < 12; j++) { c12[j] = 0; hist[j] = 0; }
+    unsigned long long rpos = 0; uint32_t rbytes = 0;
+
+    if (u < n_units && p.ctl[1] == 0xFFFFFFFFu) {
+        const uint32_t fi = (uint32_t)(u / C), ch = (uint32_t)(u % C);
+        const DecFrame fr = p.frames[fi];
+        const DecUnit un = p.units[u];
+        const uint32_t type = fr.type_flags & 0xFFu, flags = (fr.type_flags >> 8) & 0xFFu;
+        L.n = fr.n;
+        L.ms = C == 2 && (flags & 1u);
+        L.outp = p.out + (size_t)p.base[fi] * C + ch;
+        const unsigned long long ch_end = un.pos + un.size;
+        if (type == FT_RAW) {                              // reader.rs:182-188
+            const unsigned long long need = 2ull * fr.n;
+            L.pcm_bytes = (uint32_t)(need < un.size ? need : un.size);
+            L.pcm = f + un.pos;
+            if (L.pcm_bytes) L.src = M_PCM;
+        } else if (type >= 1 && type <= 12) {              // reader.rs:207-244
+            unsigned long long pos = un.pos;
+            bool ok = true;
+            auto eof = [&](unsigned long long need_end) { if (need_end > p.len) { dec_fail(p.ctl, fi, ch + 1, DEC_EOF); ok = false; } return !ok; };
+            uint32_t order = 0, ncoef = 0, shift = 0, eb = 0, k = 0;
+            if (!eof(pos + 1)) {
+                order = f[pos++];
+                if (order > 12) { dec_fail(p.ctl, fi, ch + 1, DEC_BAD_ORDER); ok = false; }
+            }
+            if (ok) {                                      // coefficients stop at the channel end (reader.rs:218-223)
+                const unsigned long long fit = ch_end > pos ? (ch_end - pos) / 4 : 0;
+                ncoef = fit < order ? (uint32_t)fit : order;
+                if (!eof(pos + 4ull * ncoef)) {
+                    #pragma unroll
+                    for (int j = 0; j < 12; j++) if ((uint32_t)j < ncoef) c12[j] = (int32_t)rd32(f + pos + 4 * j);
+                    pos += 4ull * ncoef;
+                }
+            }
+            if (ok && !eof(pos + 1)) shift = f[pos++];
+            if (ok && !eof(pos + 1)) eb = f[pos++];
+            if (ok && eb == 0 && !eof(pos + 1)) k = f[pos++];        // rice parameter only for ResidualEncoding::Rice
+            const unsigned long long rem = ok && ch_end > pos ? ch_end - pos : 0;
+            if (ok && rem) eof(pos + rem);
+            if (ok) {                                      // decode_channel_int (decoder.rs:92-148)
+                if (ncoef == 0 && rem && shift >= 128) {
+                    const uint32_t fo = shift - 128;
+                    L.src = M_RICE;
+                    if (fo >= 1 && fo <= 4) {              // other orders copy the residuals (decoder.rs:195-198, 261-264)
+                        L.fixed = true; L.order = (int)fo;
+                        #pragma unroll
+                        for (int j = 0; j < 4; j++) c12[j] = c_fixed[fo][j];
+                    }
+                } else if (ncoef) {
+                    L.src = M_RICE; L.order = (int)ncoef; L.shift = (int)(shift & 63u);
+                } else if (rem) {                          // raw PCM inside an ALPC frame (decoder.rs:132-144)
+                    L.src = M_PCM; L.pcm = f + pos;
+                    const unsigned long long need = 2ull * fr.n;
+                    L.pcm_bytes = (uint32_t)(need < rem ? need : rem);
+                }
+                if (L.src == M_RICE) {
+                    rpos = pos; rbytes = (uint32_t)rem; L.k = rem ? k : 0;     // no bytes: every residual is 0 (rice.rs:128-131)
+                    if (L.k > 31) { dec_fail(p.ctl, fi, ch + 1, DEC_BAD_K); ok = false; }
+                }
+            }
+            if (!ok) {
+                L.src = M_ZERO; L.order = 0; L.shift = 0; L.fixed = false; L.k = 0;
+                #pragma unroll
+                for (int j = 0; j < 12; j++) c12[j] = 0;
+            }
+        }
+        // Silence / reserved types: zeros (reader.rs:180, 246)
+    }
+    bits_init(L.bits, f, p.len, L.src == M_RICE ? rpos : 0ull, L.src == M_RICE ? rbytes : 0u);
+
+    const uint32_t nmax = __reduce_max_sync(FULL, L.n);
+    const int omax = (int)__reduce_max_sync(FULL, (uint32_t)L.order);
+    uint32_t i = 0;
+    const uint32_t warm = nmax < 12u ? nmax : 12u;
+    for (; i < warm; i++) synth_step(L, i, c12, hist);
+    if (omax <= 4) i = synth_blocks<4>(L, i, nmax, c12, hist);
+    else if (omax <= 8) i = synth_blocks<8>(L, i, nmax, c12, hist);
+    else i = synth_blocks<12>(L, i, nmax, c12, hist);
+    for (; i < nmax; i++) synth_step(L, i, c12, hist);
+}
+
+}  // namespace
+
+cudaError_t launch_decode_parse(const DecodeParams &p, cudaStream_t st) {
+    if (p.n_toc) k_dec_parse<<<(p.n_toc + 127) / 128, 128, 0, st>>>(p);
+    k_dec_scan<<<1, 1024, 0, st>>>(p);
+    return cudaGetLastError();
+}
+cudaError_t launch_decode_units(const DecodeParams &p, cudaStream_t st) {
+    const unsigned long long units = (unsigned long long)p.n_toc * p.channels;
+    if (units) k_dec_units<<<(unsigned)((units + 31) / 32), 32, 0, st>>>(p);
+    return cudaGetLastError();
+}
+
+}  // namespace flo

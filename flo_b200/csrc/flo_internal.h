@@ -104,5 +104,26 @@ cudaError_t launch_crc_segments(const FinalParams &p, cudaStream_t st);
 cudaError_t launch_headers(const FinalParams &p, cudaStream_t st);
 void upload_crc_tables();
 
+// ---- lossless decoder (libflo/src/reader.rs + libflo/src/lossless/decoder.rs) ----
+enum DecErr : uint32_t { DEC_TOO_MANY = 1, DEC_BAD_ORDER = 2, DEC_EOF = 3, DEC_TRANSFORM = 4, DEC_BAD_K = 5 };
+struct DecFrame { uint32_t type_flags; uint32_t n; };          // type | flags << 8 ; frame_samples (0 past the reader's break)
+struct DecUnit  { unsigned long long pos; uint32_t size; uint32_t pad; };   // one channel of one frame: payload position and ch_size
+struct DecodeParams {
+    const uint8_t *file;              // file image in device memory; readable up to the next 16-byte boundary after file + len
+    unsigned long long len;
+    unsigned long long toc_pos;       // first TOC entry (host checked that the TOC lies inside the file)
+    uint32_t n_toc;
+    uint32_t channels;
+    unsigned long long data_start, data_end;
+    DecFrame *frames;                 // [n_toc]
+    DecUnit *units;                   // [n_toc * channels]
+    unsigned long long *base;         // [n_toc] exclusive prefix of frame_samples
+    uint32_t *ctl;                    // [0] index of the first TOC entry the reader breaks on (init n_toc), [1] smallest error key
+                                      // (init 0xFFFFFFFF; frame << 13 | (channel + 1) << 4 | DecErr), [2..3] total sample frames (u64)
+    float *out;                       // interleaved f32, total * channels
+};
+cudaError_t launch_decode_parse(const DecodeParams &p, cudaStream_t st);   // parse + scan (2 kernels)
+cudaError_t launch_decode_units(const DecodeParams &p, cudaStream_t st);   // 1 kernel
+
 
 }  // namespace flo

@@ -10,6 +10,7 @@ from __future__ import annotations
 
 import ctypes as C
 import threading
+import weakref
 from dataclasses import dataclass
 from typing import List, Optional, Sequence, Tuple
 
@@ -128,6 +129,29 @@ class Context:
             off.ctypes.data_as(C.POINTER(C.c_uint64)), ln.ctypes.data_as(C.POINTER(C.c_uint64))))
         return off, ln
 
+    # -- lossless decoder (include/flo_b200.h: flo_decode / flo_decode_device) ---------
+    def decode(self, data) -> Tuple[np.ndarray, dict]:
+        """Decoder::decode (libflo/src/lossless/decoder.rs:14-18): interleaved f32 samples + header info.
+        The array is a zero-copy view of the library's (pinned) result block, released with the array."""
+        buf = np.frombuffer(data, dtype=np.uint8) if not isinstance(data, np.ndarray) else np.ascontiguousarray(data, dtype=np.uint8)
+        out, n, info = C.c_void_p(), C.c_size_t(), _lib.Info()
+        ptr = buf.ctypes.data if buf.size else C.addressof(C.create_string_buffer(1))
+        _lib.check(self._L.flo_decode(self._h, C.c_void_p(ptr), buf.size, C.byref(out), C.byref(n), C.byref(info)))
+        if n.value == 0:
+            self._L.flo_free(out)
+            return np.zeros(0, dtype=np.float32), _info_dict(info)
+        raw = (C.c_float * n.value).from_address(out.value)
+        weakref.finalize(raw, self._L.flo_free, C.c_void_p(out.value))
+        return np.frombuffer(raw, dtype=np.float32), _info_dict(info)
+
+    def decode_device(self, d_file: int, length: int, d_out: int, capacity: int) -> Tuple[int, dict]:
+        """Device-resident decode: `d_file` / `d_out` are device pointers (capacity in floats).
+        Returns (interleaved sample count, info)."""
+        n, info = C.c_size_t(), _lib.Info()
+        _lib.check(self._L.flo_decode_device(self._h, C.c_void_p(int(d_file)), int(length), C.c_void_p(int(d_out) or None),
+                                             int(capacity), C.byref(n), C.byref(info)))
+        return int(n.value), _info_dict(info)
+
     def output_bound(self, n_interleaved: Sequence[int], sample_rate: Sequence[int], channels: Sequence[int],
                      meta_len: Optional[Sequence[int]] = None) -> int:
         n = len(n_interleaved)
@@ -144,6 +168,10 @@ class Context:
         if b == 0:
             raise FloError(_lib.last_error())
         return b + extra
+
+
+def _info_dict(info) -> dict:
+    return {k: int(getattr(info, k)) for k, _ in _lib.Info._fields_}
 
 
 class BatchResult:
@@ -247,3 +275,23 @@ class Encoder:
 def encode_batch(tracks: Sequence[TrackSpec], level: int = 5, fmt: int = FMT_F32, device: int = 0) -> List[bytes]:
     """Loop of Encoder::encode over tracks (reflo/src/main.rs:218-276) as one device pass."""
     return default_context(device).encode_batch(tracks, min(int(level), 9), fmt)
+
+
+class Decoder:
+    """libflo_audio::Decoder (libflo/src/lossless/decoder.rs:6-18): `Decoder().decode(data) -> samples`."""
+
+    def __init__(self, *, device: int = 0, context: Optional[Context] = None):
+        self._device = device
+        self._ctx = context
+
+    def _context(self) -> Context:
+        if self._ctx is None:
+            self._ctx = default_context(self._device)
+        return self._ctx
+
+    def decode(self, data) -> np.ndarray:
+        """Decoder::decode(&self, data: &[u8]) -> FloResult<Vec<f32>>: interleaved f32 samples."""
+        return self._context().decode(data)[0]
+
+    def decode_with_info(self, data) -> Tuple[np.ndarray, dict]:
+        return self._context().decode(data)

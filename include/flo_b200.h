@@ -124,6 +124,32 @@ typedef struct { int32_t k; int32_t pad; int64_t size; } flo_cand_report;
 int flo_ctx_enable_report(flo_ctx *ctx, int enable);
 int flo_ctx_read_report(flo_ctx *ctx, uint32_t frame, uint32_t channel, flo_cand_report out[14]);
 
+/* ---- lossless decoder (companion of the encode path) ----
+ * Decoder::decode(&self, data: &[u8]) -> FloResult<Vec<f32>> (libflo/src/lossless/decoder.rs:14-18) over
+ * Reader::read (libflo/src/reader.rs:16-53): interleaved f32 samples, sample * (1/32767)
+ * (core/audio_constants.rs:24-26).  Errors carry the reference's messages ("Invalid flo file: bad magic",
+ * "Unexpected end of file", "Invalid TOC: too many entries", "Invalid frame: too many samples",
+ * "Invalid LPC order") through flo_last_error().  Files holding transform (lossy) frames are refused. */
+typedef struct {
+    uint32_t sample_rate;
+    uint8_t  channels, bit_depth, level, version_major;
+    uint64_t total_samples;        /* header field (sample frames per channel) */
+    uint64_t decoded_frames;       /* sample frames decoded = sum of frame_samples over the frames read */
+    uint32_t n_frames;             /* frames read (reader.rs:116-118 may stop early) */
+    uint32_t data_crc32;           /* header field; not verified (the reference decoder does not either) */
+    uint64_t meta_offset, meta_size;
+} flo_info;
+
+/* *out is library-allocated (flo_free); *n_interleaved = decoded_frames * channels.  info may be NULL. */
+int flo_decode(flo_ctx *ctx, const uint8_t *file, size_t len, float **out, size_t *n_interleaved, flo_info *info);
+
+/* Device-resident variant: d_file is a DEVICE pointer to the file image (readable up to the next 16-byte
+ * boundary past its end -- true for any image inside a cudaMalloc'd buffer, e.g. flo_encode_batch_device
+ * output); samples are written to the device buffer d_out (capacity in floats).  When the capacity is too
+ * small the call fails with FLO_ERR_ARG and *n_interleaved holds the count needed. */
+int flo_decode_device(flo_ctx *ctx, const void *d_file, size_t len, float *d_out, size_t d_out_capacity,
+                      size_t *n_interleaved, flo_info *info);
+
 /* Pinned host memory (optional; speeds up the host<->device copies of
  * flo_encode / flo_encode_batch when inputs live in it). */
 void *flo_host_alloc(size_t bytes);

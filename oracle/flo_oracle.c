@@ -668,6 +668,11 @@ flo_ref_file *flo_ref_parse(const uint8_t *data, size_t len) { /* reader.rs:16-1
         }
         c.pos = fend;
     }
+    /* reader.rs:35-43: cursor at the end of DATA, EXTRA skipped (clamped to the file), META read in full */
+    c.pos = data_end;
+    c_skip(&c, (size_t)f->extra_size);
+    if (c.pos > len) c.pos = len;
+    if ((size_t)f->meta_size > len - c.pos) { set_err("Unexpected end of file"); flo_ref_file_free(f); return NULL; }
     return f;
 }
 

@@ -31,6 +31,22 @@ pub struct flo_cand_report {
     pub size: i64,
 }
 
+#[repr(C)]
+#[derive(Default, Clone, Copy, Debug)]
+pub struct flo_info {
+    pub sample_rate: u32,
+    pub channels: u8,
+    pub bit_depth: u8,
+    pub level: u8,
+    pub version_major: u8,
+    pub total_samples: u64,
+    pub decoded_frames: u64,
+    pub n_frames: u32,
+    pub data_crc32: u32,
+    pub meta_offset: u64,
+    pub meta_size: u64,
+}
+
 pub const FLO_FMT_F32: c_int = 0;
 pub const FLO_FMT_PCM16: c_int = 1;
 
@@ -48,6 +64,10 @@ extern "C" {
     pub fn flo_encode_batch_device(ctx: *mut flo_ctx, tracks: *const flo_track, n_tracks: usize, format: c_int,
                                    level: u8, d_out: *mut c_void, d_out_capacity: usize,
                                    offsets: *mut u64, lens: *mut u64) -> c_int;
+    pub fn flo_decode(ctx: *mut flo_ctx, file: *const u8, len: usize, out: *mut *mut f32, n_interleaved: *mut usize,
+                      info: *mut flo_info) -> c_int;
+    pub fn flo_decode_device(ctx: *mut flo_ctx, d_file: *const c_void, len: usize, d_out: *mut f32,
+                             d_out_capacity: usize, n_interleaved: *mut usize, info: *mut flo_info) -> c_int;
     pub fn flo_output_bound(tracks: *const flo_track, n_tracks: usize) -> usize;
     pub fn flo_ctx_set_stream(ctx: *mut flo_ctx, cuda_stream: *mut c_void) -> c_int;
     pub fn flo_ctx_last_timing(ctx: *mut flo_ctx, ms: *mut f32, launches: *mut u32) -> c_int;

@@ -133,3 +133,31 @@ pub fn encode_batch(ctx: &Arc<Context>, tracks: &[TrackRef<'_>], level: u8) -> F
         v
     }).collect())
 }
+
+/// `libflo_audio::Decoder` (libflo/src/lossless/decoder.rs:6-18) over `flo_decode`.
+#[derive(Default)]
+pub struct Decoder {
+    ctx: Option<Arc<Context>>,
+}
+
+impl Decoder {
+    pub fn new() -> Self {
+        Decoder { ctx: None }
+    }
+
+    pub fn with_context(mut self, ctx: Arc<Context>) -> Self {
+        self.ctx = Some(ctx);
+        self
+    }
+
+    /// decoder.rs:14-18: interleaved f32 samples.
+    pub fn decode(&self, data: &[u8]) -> FloResult<Vec<f32>> {
+        let ctx = match &self.ctx { Some(c) => c.clone(), None => Context::default_device()? };
+        let (mut out, mut n) = (ptr::null_mut::<f32>(), 0usize);
+        let rc = unsafe { ffi::flo_decode(ctx.0, data.as_ptr(), data.len(), &mut out, &mut n, ptr::null_mut()) };
+        if rc != 0 { return Err(last_error()); }
+        let v = unsafe { std::slice::from_raw_parts(out, n).to_vec() };
+        unsafe { ffi::flo_free(out as *mut _) };
+        Ok(v)
+    }
+}
