@@ -93,50 +93,90 @@ __global__ void __launch_bounds__(1024) k_dec_scan(DecodeParams p) {
 }
 
 // ---- bit reader: MSB-first (rice.rs:217-260), bits past the end of the payload read as 0 ----
+// Every lane reads its own stream, at its own pace.  A register written by a global load inside a divergent
+// branch would stall the whole warp on the next lane's turn (the scoreboard is per warp register), so the
+// streams are staged through shared memory instead: a 32-word ring per lane (word-interleaved, bank = lane),
+// topped up at warp-uniform points with 16-byte loads that are stored to the ring one top-up later.  The
+// per-sample path is branch-free: one predicated 32-bit append and one unconditional LDS of the next word.
+constexpr int RING = 32;              // words per lane
+constexpr int GROUP = 8;              // samples between top-ups; the fast path pops at most one word per sample
 struct BitIn {
-    const uint4 *vp, *vend;
-    uint4 cur, nx1, nx2;              // 16-byte vectors in flight: the loads run two vectors ahead of the bits in use
-    uint32_t j, left;                 // next word of `cur`; payload bytes not yet popped
+    const uint4 *gp, *vend;           // next vector to request; end of the readable image
+    uint4 p0, p1;                     // vectors in flight
+    uint32_t npend;
+    uint32_t wr, rd;                  // ring word counters: next word to store / word held in nxt
+    unsigned long long end_off;       // payload end, as a byte offset from the aligned base of the stream
+    uint32_t nxt;                     // ring[rd], loaded ahead
     unsigned long long buf;           // MSB-aligned window
     int nb;                           // bits in the window
 };
-__device__ __forceinline__ uint4 ldv(const uint4 *p, const uint4 *end) { return p < end ? __ldg(p) : make_uint4(0u, 0u, 0u, 0u); }
-__device__ __forceinline__ uint32_t pop_raw(BitIn &b) {
-    const uint32_t w = b.j == 0 ? b.cur.x : b.j == 1 ? b.cur.y : b.j == 2 ? b.cur.z : b.cur.w;
-    if (++b.j == 4) { b.j = 0; b.cur = b.nx1; b.nx1 = b.nx2; b.nx2 = ldv(b.vp, b.vend); b.vp++; }
-    return __byte_perm(w, 0u, 0x0123);
+// Past the end of the image the address is clamped (the bytes are masked off in put_vec anyway): nothing may
+// depend on the loaded registers until the next top-up stores them.
+__device__ __forceinline__ uint4 ldv(const uint4 *p, const uint4 *end) { return __ldg(p < end ? p : end - 1); }
+__device__ __forceinline__ uint32_t be_masked(uint32_t raw, unsigned long long pos, unsigned long long end_off) {
+    const uint32_t w = __byte_perm(raw, 0u, 0x0123);
+    if (pos + 4 <= end_off) return w;
+    return pos >= end_off ? 0u : (w & ~(0xFFFFFFFFu >> (8u * (uint32_t)(end_off - pos))));
 }
-__device__ __forceinline__ uint32_t pop(BitIn &b) {
-    const uint32_t w = pop_raw(b);
-    const uint32_t valid = b.left < 4u ? b.left : 4u;
-    b.left -= valid;
-    return valid == 4u ? w : (w & ~(0xFFFFFFFFu >> (8u * valid)));
+__device__ __forceinline__ void put_vec(uint32_t *ring, uint32_t lane, BitIn &b, const uint4 &v) {
+    uint32_t *slot = ring + ((b.wr & (RING - 1)) << 5) + lane;        // wr is a multiple of 4: the four slots do not wrap
+    const unsigned long long pos = 4ull * b.wr;
+    if (pos + 16 <= b.end_off) {
+        slot[0] = __byte_perm(v.x, 0u, 0x0123); slot[32] = __byte_perm(v.y, 0u, 0x0123);
+        slot[64] = __byte_perm(v.z, 0u, 0x0123); slot[96] = __byte_perm(v.w, 0u, 0x0123);
+    } else {                                               // the payload ends inside this vector: later bytes read as 0
+        slot[0] = be_masked(v.x, pos, b.end_off); slot[32] = be_masked(v.y, pos + 4, b.end_off);
+        slot[64] = be_masked(v.z, pos + 8, b.end_off); slot[96] = be_masked(v.w, pos + 12, b.end_off);
+    }
+    b.wr += 4;
 }
-__device__ __forceinline__ void bits_init(BitIn &b, const uint8_t *file, unsigned long long len, unsigned long long start, uint32_t nbytes) {
+__device__ __forceinline__ void topup_once(uint32_t *ring, uint32_t lane, BitIn &b) {
+    if (b.npend >= 1) put_vec(ring, lane, b, b.p0);
+    if (b.npend == 2) put_vec(ring, lane, b, b.p1);
+    b.npend = 0;
+    const uint32_t room = RING - (b.wr - b.rd);
+    if (room >= 4) { b.p0 = ldv(b.gp, b.vend); b.gp++; b.npend = 1; }
+    if (room >= 8) { b.p1 = ldv(b.gp, b.vend); b.gp++; b.npend = 2; }
+}
+// Warp-uniform.  Afterwards every lane holds at least 2 * GROUP words, so the fast path cannot run dry before the next call.
+__device__ __forceinline__ void topup(uint32_t *ring, uint32_t lane, BitIn &b) {
+    do topup_once(ring, lane, b);
+    while (__any_sync(FULL, b.wr - b.rd < 2 * GROUP));      // rare second trip: waits for the loads just issued
+}
+__device__ __forceinline__ void bits_init(uint32_t *ring, uint32_t lane, BitIn &b, const uint8_t *file, unsigned long long len,
+                                          unsigned long long start, uint32_t nbytes) {
     const uintptr_t a = (uintptr_t)(file + start), a0 = a & ~(uintptr_t)15;
+    const uint32_t sk = (uint32_t)(a - a0);
     b.vend = (const uint4 *)(((uintptr_t)(file + len) + 15) & ~(uintptr_t)15);
-    b.vp = nbytes ? (const uint4 *)a0 : b.vend;
-    b.cur = ldv(b.vp, b.vend); b.vp++;
-    b.nx1 = ldv(b.vp, b.vend); b.vp++;
-    b.nx2 = ldv(b.vp, b.vend); b.vp++;
-    const uint32_t sk = (uint32_t)(a - a0), sb = sk & 3u;
-    b.j = sk >> 2;
-    b.left = nbytes; b.buf = 0; b.nb = 0;
-    if (sb) {                          // payload starts inside a word
-        uint32_t w = pop_raw(b) << (8u * sb);
-        const uint32_t room = 4u - sb, valid = b.left < room ? b.left : room;
-        b.left -= valid;
-        w &= ~(0xFFFFFFFFu >> (8u * valid));
-        b.buf = (unsigned long long)w << 32;
-        b.nb = 32 - 8 * (int)sb;
+    b.gp = nbytes ? (const uint4 *)a0 : b.vend;
+    b.end_off = (unsigned long long)sk + nbytes;
+    b.npend = 0; b.wr = 0; b.rd = 0;
+    b.p0 = b.p1 = make_uint4(0u, 0u, 0u, 0u);
+    topup(ring, lane, b);
+    b.rd = sk >> 2;                                        // the payload starts sk bytes into the first vector
+    const uint32_t sb = sk & 3u;
+    const uint32_t w = ring[((b.rd & (RING - 1)) << 5) + lane];
+    b.rd++;
+    b.buf = sb ? (unsigned long long)(w << (8u * sb)) << 32 : (unsigned long long)w << 32;
+    b.nb = 32 - 8 * (int)sb;
+    b.nxt = ring[((b.rd & (RING - 1)) << 5) + lane];
+}
+// lane-private (divergent) fill: at least `want` words on hand; fetches synchronously when the ring is dry
+__device__ __forceinline__ void lane_fill(uint32_t *ring, uint32_t lane, BitIn &b, int want) {
+    while ((int)(b.wr - b.rd) < want) {
+        if (b.npend) { put_vec(ring, lane, b, b.p0); if (b.npend == 2) put_vec(ring, lane, b, b.p1); b.npend = 0; }
+        else { b.p0 = ldv(b.gp, b.vend); b.gp++; b.npend = 1; }
     }
 }
-__device__ __forceinline__ void refill(BitIn &b) {
-    if (b.nb <= 32) { b.buf |= (unsigned long long)pop(b) << (32 - b.nb); b.nb += 32; }
+__device__ __forceinline__ void refill_checked(uint32_t *ring, uint32_t lane, BitIn &b) {
+    if (b.nb > 32) return;
+    b.buf |= (unsigned long long)b.nxt << (32 - b.nb); b.nb += 32; b.rd++;
+    lane_fill(ring, lane, b, 1);
+    b.nxt = ring[((b.rd & (RING - 1)) << 5) + lane];
 }
 // decode_i32's loop body (rice.rs:127-155): unary quotient (ones, capped at 256 reads), k-bit remainder, zigzag.
 // Rare path: the code does not fit the bits on hand (long unary run, large k).
-__device__ __forceinline__ uint32_t rice_slow(BitIn &b, uint32_t k) {
+__device__ __forceinline__ uint32_t rice_slow(uint32_t *ring, uint32_t lane, BitIn &b, uint32_t k) {
     uint32_t q = 0;
     for (;;) {
         int run = __clzll((long long)~b.buf);
@@ -150,24 +190,35 @@ __device__ __forceinline__ uint32_t rice_slow(BitIn &b, uint32_t k) {
         q += (uint32_t)run;
         if (!more) { b.buf = (b.buf << run) << 1; b.nb -= run + 1; break; }
         b.buf = 0; b.nb = 0;
-        refill(b);
+        refill_checked(ring, lane, b);
     }
-    refill(b);
+    refill_checked(ring, lane, b);
     uint32_t r = 0;
     if (k) { r = (uint32_t)(b.buf >> (64 - k)); b.buf <<= k; b.nb -= (int)k; }
+    lane_fill(ring, lane, b, GROUP + 1);                   // the rest of this group pops without checking
+    b.nxt = ring[((b.rd & (RING - 1)) << 5) + lane];
     return (q << k) | r;
 }
-__device__ __forceinline__ int32_t rice_next(BitIn &b, uint32_t k) {
-    refill(b);                                             // 33..64 bits on hand; unused low bits of the window are 0
-    const int run = __clzll((long long)~b.buf);            // leading ones
+// Common path, branch-free up to the fit test: append the word on hand when the window is half empty, count the
+// leading ones of the top word, cut the k remainder bits out with funnel shifts.
+__device__ __forceinline__ int32_t rice_next(uint32_t *ring, uint32_t lane, BitIn &b, uint32_t k) {
+    const bool need = b.nb <= 32;                          // then the low word of the window is empty
+    const uint32_t hi0 = (uint32_t)(b.buf >> 32);
+    const uint32_t hi = need ? (hi0 | __funnelshift_rc(b.nxt, 0u, (uint32_t)b.nb)) : hi0;
+    const uint32_t lo = need ? __funnelshift_lc(0u, b.nxt, 32u - (uint32_t)b.nb) : (uint32_t)b.buf;
+    b.nb += need ? 32 : 0;
+    b.rd += need ? 1u : 0u;
+    b.nxt = ring[((b.rd & (RING - 1)) << 5) + lane];       // not needed before the next sample
+    const int run = __clz((int)~hi);                       // leading ones (32: the run leaves the top word)
     const int used = run + 1 + (int)k;
+    b.buf = ((unsigned long long)hi << 32) | lo;
     uint32_t u;
-    if (__builtin_expect(used <= b.nb, 1)) {
-        const unsigned long long t = (b.buf << run) << 1;
-        u = ((uint32_t)run << k) | (uint32_t)((t >> 1) >> (63 - k));
-        b.buf = t << k; b.nb -= used;
+    if (__builtin_expect(run < 32 && used <= b.nb, 1)) {
+        const uint32_t t = __funnelshift_lc(lo, hi, (uint32_t)(run + 1));
+        u = ((uint32_t)run << k) | __funnelshift_rc(t, 0u, 32u - k);
+        b.buf <<= used; b.nb -= used;                      // used <= 63
     } else {
-        u = rice_slow(b, k);
+        u = rice_slow(ring, lane, b, k);
     }
     return (int32_t)(u >> 1) ^ -(int32_t)(u & 1u);
 }
@@ -178,6 +229,8 @@ enum { M_ZERO = 0, M_RICE = 1, M_PCM = 2 };
 
 struct Lane {
     BitIn bits;
+    uint32_t *ring; uint32_t lane;
+    bool any_pcm;                     // warp-uniform: some lane reads raw PCM
     const uint8_t *pcm; uint32_t pcm_bytes;
     float *outp; uint32_t stride;
     uint32_t n, k;
@@ -187,16 +240,16 @@ struct Lane {
 };
 
 __device__ __forceinline__ int32_t next_residual(Lane &L, uint32_t i) {
-    int32_t r = rice_next(L.bits, L.k);
-    if (L.src == M_PCM) {             // decoder.rs:132-143
+    int32_t r = rice_next(L.ring, L.lane, L.bits, L.k);
+    if (L.src == M_PCM) {                                  // decoder.rs:132-143
         r = 0;
         if (2ull * i + 1 < L.pcm_bytes) r = (int16_t)((uint16_t)__ldg(L.pcm + 2ull * i) | ((uint16_t)__ldg(L.pcm + 2ull * i + 1) << 8));
     }
     return r;
 }
-// mid/side inverse (decoder.rs:75-89), i32 -> f32 (audio_constants.rs:24-26), interleaved store
-__device__ __forceinline__ void emit(const Lane &L, uint32_t i, int32_t s) {
-    const int32_t o = __shfl_xor_sync(FULL, s, 1);
+// mid/side inverse (decoder.rs:75-89), i32 -> f32 (audio_constants.rs:24-26), interleaved store.
+// `o` is the neighbour lane's sample (the other channel of a stereo frame).
+__device__ __forceinline__ void emit_pair(const Lane &L, uint32_t i, int32_t s, int32_t o) {
     int32_t v = s;
     if (L.ms) {
         const uint32_t m = (uint32_t)(L.odd ? o : s), d = (uint32_t)(L.odd ? s : o);
@@ -204,28 +257,38 @@ __device__ __forceinline__ void emit(const Lane &L, uint32_t i, int32_t s) {
     }
     if (i < L.n) L.outp[(size_t)i * L.stride] = __fmul_rn(__int2float_rn(v), 1.0f / 32767.0f);
 }
+__device__ __forceinline__ void emit(const Lane &L, uint32_t i, int32_t s) { emit_pair(L, i, s, __shfl_xor_sync(FULL, s, 1)); }
 
-// Steady state for predictors of at most ORD taps: history newest-first in ORD registers.  The loop is kept
-// rolled (one sample per trip, ORD register moves) so that its body stays inside the instruction cache --
-// with one warp per scheduler nothing else hides a fetch miss.
+// Steady state for Rice-coded lanes with predictors of at most ORD taps: history newest-first in ORD registers,
+// GROUP samples per trip (one ring top-up per trip).  The per-sample loop stays rolled so that there is one copy
+// of the bit reader; the neighbour shuffle of sample i is consumed while sample i + 1 is decoded.
 template <int ORD>
 __device__ __forceinline__ uint32_t synth_blocks(Lane &L, uint32_t i, uint32_t nmax, const int32_t (&c12)[12], int32_t (&hist)[12]) {
+    if (i + GROUP > nmax) return i;
     int32_t c[ORD], h[ORD];
     #pragma unroll
     for (int j = 0; j < ORD; j++) { c[j] = c12[j]; h[j] = hist[j]; }
     const int sh = L.shift;
+    int32_t s_prev = 0, o_prev = 0;
+    bool have_prev = false;
     #pragma unroll 1
-    for (; i < nmax; i++) {
-        const int32_t r = next_residual(L, i);
-        long long acc = 0;
-        #pragma unroll
-        for (int j = ORD - 1; j >= 0; j--) acc += (long long)c[j] * (long long)h[j];    // newest sample last: shortest carried chain
-        const int32_t s = (int32_t)((uint32_t)(int32_t)(acc >> sh) + (uint32_t)r);
-        #pragma unroll
-        for (int j = ORD - 1; j > 0; j--) h[j] = h[j - 1];
-        h[0] = s;
-        emit(L, i, s);
+    for (; i + GROUP <= nmax; i += GROUP) {
+        topup(L.ring, L.lane, L.bits);
+        #pragma unroll 1
+        for (int t = 0; t < GROUP; t++) {
+            const int32_t r = rice_next(L.ring, L.lane, L.bits, L.k);
+            long long acc = 0;
+            #pragma unroll
+            for (int j = ORD - 1; j >= 0; j--) acc += (long long)c[j] * (long long)h[j];    // newest sample last: shortest carried chain
+            const int32_t s = (int32_t)((uint32_t)(int32_t)(acc >> sh) + (uint32_t)r);
+            #pragma unroll
+            for (int j = ORD - 1; j > 0; j--) h[j] = h[j - 1];
+            h[0] = s;
+            if (have_prev) emit_pair(L, i + t - 1, s_prev, o_prev);
+            s_prev = s; o_prev = __shfl_xor_sync(FULL, s, 1); have_prev = true;
+        }
     }
+    emit_pair(L, i - 1, s_prev, o_prev);
     #pragma unroll
     for (int j = 0; j < ORD; j++) hist[j] = h[j];
     return i;
@@ -233,6 +296,7 @@ __device__ __forceinline__ uint32_t synth_blocks(Lane &L, uint32_t i, uint32_t n
 
 // Generic step with the history newest-first in hist[]: warm-up rules (decoder.rs:163-165, 199-259) and block tails.
 __device__ __forceinline__ void synth_step(Lane &L, uint32_t i, const int32_t (&c12)[12], int32_t (&hist)[12]) {
+    topup(L.ring, L.lane, L.bits);
     const int32_t r = next_residual(L, i);
     int32_t pred = 0;
     if (i >= (uint32_t)L.order) {
@@ -254,6 +318,7 @@ __device__ __forceinline__ void synth_step(Lane &L, uint32_t i, const int32_t (&
 }
 
 __global__ void __launch_bounds__(32) k_dec_units(DecodeParams p) {
+    __shared__ uint32_t ring[RING * 32];
     const uint32_t lane = threadIdx.x;
     const unsigned long long u = (unsigned long long)blockIdx.x * 32 + lane;
     const uint32_t C = p.channels;
@@ -335,16 +400,20 @@ __global__ void __launch_bounds__(32) k_dec_units(DecodeParams p) {
         }
         // Silence / reserved types: zeros (reader.rs:180, 246)
     }
-    bits_init(L.bits, f, p.len, L.src == M_RICE ? rpos : 0ull, L.src == M_RICE ? rbytes : 0u);
+    L.ring = ring; L.lane = lane;
+    L.any_pcm = __any_sync(FULL, L.src == M_PCM);
+    bits_init(ring, lane, L.bits, f, p.len, L.src == M_RICE ? rpos : 0ull, L.src == M_RICE ? rbytes : 0u);
 
     const uint32_t nmax = __reduce_max_sync(FULL, L.n);
     const int omax = (int)__reduce_max_sync(FULL, (uint32_t)L.order);
     uint32_t i = 0;
     const uint32_t warm = nmax < 12u ? nmax : 12u;
     for (; i < warm; i++) synth_step(L, i, c12, hist);
-    if (omax <= 4) i = synth_blocks<4>(L, i, nmax, c12, hist);
-    else if (omax <= 8) i = synth_blocks<8>(L, i, nmax, c12, hist);
-    else i = synth_blocks<12>(L, i, nmax, c12, hist);
+    if (!L.any_pcm) {                                      // raw PCM lanes (rare) take the generic step for the whole warp
+        if (omax <= 4) i = synth_blocks<4>(L, i, nmax, c12, hist);
+        else if (omax <= 8) i = synth_blocks<8>(L, i, nmax, c12, hist);
+        else i = synth_blocks<12>(L, i, nmax, c12, hist);
+    }
     for (; i < nmax; i++) synth_step(L, i, c12, hist);
 }
 
