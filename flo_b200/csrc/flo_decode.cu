@@ -113,22 +113,26 @@ struct BitIn {
 // Past the end of the image the address is clamped (the bytes are masked off in put_vec anyway): nothing may
 // depend on the loaded registers until the next top-up stores them.
 __device__ __forceinline__ uint4 ldv(const uint4 *p, const uint4 *end) { return __ldg(p < end ? p : end - 1); }
-__device__ __forceinline__ uint32_t be_masked(uint32_t raw, unsigned long long pos, unsigned long long end_off) {
-    const uint32_t w = __byte_perm(raw, 0u, 0x0123);
-    if (pos + 4 <= end_off) return w;
-    return pos >= end_off ? 0u : (w & ~(0xFFFFFFFFu >> (8u * (uint32_t)(end_off - pos))));
+// Words go into the ring as loaded (little-endian); the pop side byte-swaps.  Nothing here may touch the loaded
+// registers except the stores themselves, or the compiler hoists that work to right behind the loads and the
+// warp waits out the full memory latency at every top-up.
+__device__ __forceinline__ uint32_t le_masked(uint32_t raw, unsigned long long pos, unsigned long long end_off) {
+    if (pos + 4 <= end_off) return raw;
+    return pos >= end_off ? 0u : (raw & ~(0xFFFFFFFFu << (8u * (uint32_t)(end_off - pos))));
 }
 __device__ __forceinline__ void put_vec(uint32_t *ring, uint32_t lane, BitIn &b, const uint4 &v) {
     uint32_t *slot = ring + ((b.wr & (RING - 1)) << 5) + lane;        // wr is a multiple of 4: the four slots do not wrap
     const unsigned long long pos = 4ull * b.wr;
     if (pos + 16 <= b.end_off) {
-        slot[0] = __byte_perm(v.x, 0u, 0x0123); slot[32] = __byte_perm(v.y, 0u, 0x0123);
-        slot[64] = __byte_perm(v.z, 0u, 0x0123); slot[96] = __byte_perm(v.w, 0u, 0x0123);
+        slot[0] = v.x; slot[32] = v.y; slot[64] = v.z; slot[96] = v.w;
     } else {                                               // the payload ends inside this vector: later bytes read as 0
-        slot[0] = be_masked(v.x, pos, b.end_off); slot[32] = be_masked(v.y, pos + 4, b.end_off);
-        slot[64] = be_masked(v.z, pos + 8, b.end_off); slot[96] = be_masked(v.w, pos + 12, b.end_off);
+        slot[0] = le_masked(v.x, pos, b.end_off); slot[32] = le_masked(v.y, pos + 4, b.end_off);
+        slot[64] = le_masked(v.z, pos + 8, b.end_off); slot[96] = le_masked(v.w, pos + 12, b.end_off);
     }
     b.wr += 4;
+}
+__device__ __forceinline__ uint32_t ring_word(const uint32_t *ring, uint32_t lane, uint32_t idx) {
+    return __byte_perm(ring[((idx & (RING - 1)) << 5) + lane], 0u, 0x0123);             // big-endian: MSB first
 }
 __device__ __forceinline__ void topup_once(uint32_t *ring, uint32_t lane, BitIn &b) {
     if (b.npend >= 1) put_vec(ring, lane, b, b.p0);
@@ -155,11 +159,11 @@ __device__ __forceinline__ void bits_init(uint32_t *ring, uint32_t lane, BitIn &
     topup(ring, lane, b);
     b.rd = sk >> 2;                                        // the payload starts sk bytes into the first vector
     const uint32_t sb = sk & 3u;
-    const uint32_t w = ring[((b.rd & (RING - 1)) << 5) + lane];
+    const uint32_t w = ring_word(ring, lane, b.rd);
     b.rd++;
     b.buf = sb ? (unsigned long long)(w << (8u * sb)) << 32 : (unsigned long long)w << 32;
     b.nb = 32 - 8 * (int)sb;
-    b.nxt = ring[((b.rd & (RING - 1)) << 5) + lane];
+    b.nxt = ring_word(ring, lane, b.rd);
 }
 // lane-private (divergent) fill: at least `want` words on hand; fetches synchronously when the ring is dry
 __device__ __forceinline__ void lane_fill(uint32_t *ring, uint32_t lane, BitIn &b, int want) {
@@ -168,15 +172,17 @@ __device__ __forceinline__ void lane_fill(uint32_t *ring, uint32_t lane, BitIn &
         else { b.p0 = ldv(b.gp, b.vend); b.gp++; b.npend = 1; }
     }
 }
-__device__ __forceinline__ void refill_checked(uint32_t *ring, uint32_t lane, BitIn &b) {
+__device__ __forceinline__ void refill_slow(uint32_t *ring, uint32_t lane, BitIn &b) {
     if (b.nb > 32) return;
     b.buf |= (unsigned long long)b.nxt << (32 - b.nb); b.nb += 32; b.rd++;
-    lane_fill(ring, lane, b, 1);
-    b.nxt = ring[((b.rd & (RING - 1)) << 5) + lane];
+    b.nxt = ring_word(ring, lane, b.rd);
 }
 // decode_i32's loop body (rice.rs:127-155): unary quotient (ones, capped at 256 reads), k-bit remainder, zigzag.
-// Rare path: the code does not fit the bits on hand (long unary run, large k).
+// Rare path: the code does not fit the bits on hand (long unary run, large k).  One code takes at most
+// 256 + 1 + 31 bits = 9 words; with 20 on hand at entry the rest of the group still pops without checking.
 __device__ __forceinline__ uint32_t rice_slow(uint32_t *ring, uint32_t lane, BitIn &b, uint32_t k) {
+    lane_fill(ring, lane, b, GROUP + 12);
+    b.nxt = ring_word(ring, lane, b.rd);
     uint32_t q = 0;
     for (;;) {
         int run = __clzll((long long)~b.buf);
@@ -190,13 +196,11 @@ __device__ __forceinline__ uint32_t rice_slow(uint32_t *ring, uint32_t lane, Bit
         q += (uint32_t)run;
         if (!more) { b.buf = (b.buf << run) << 1; b.nb -= run + 1; break; }
         b.buf = 0; b.nb = 0;
-        refill_checked(ring, lane, b);
+        refill_slow(ring, lane, b);
     }
-    refill_checked(ring, lane, b);
+    refill_slow(ring, lane, b);
     uint32_t r = 0;
     if (k) { r = (uint32_t)(b.buf >> (64 - k)); b.buf <<= k; b.nb -= (int)k; }
-    lane_fill(ring, lane, b, GROUP + 1);                   // the rest of this group pops without checking
-    b.nxt = ring[((b.rd & (RING - 1)) << 5) + lane];
     return (q << k) | r;
 }
 // Common path, branch-free up to the fit test: append the word on hand when the window is half empty, count the
@@ -208,7 +212,7 @@ __device__ __forceinline__ int32_t rice_next(uint32_t *ring, uint32_t lane, BitI
     const uint32_t lo = need ? __funnelshift_lc(0u, b.nxt, 32u - (uint32_t)b.nb) : (uint32_t)b.buf;
     b.nb += need ? 32 : 0;
     b.rd += need ? 1u : 0u;
-    b.nxt = ring[((b.rd & (RING - 1)) << 5) + lane];       // not needed before the next sample
+    b.nxt = ring_word(ring, lane, b.rd);       // not needed before the next sample
     const int run = __clz((int)~hi);                       // leading ones (32: the run leaves the top word)
     const int used = run + 1 + (int)k;
     b.buf = ((unsigned long long)hi << 32) | lo;
@@ -247,48 +251,59 @@ __device__ __forceinline__ int32_t next_residual(Lane &L, uint32_t i) {
     }
     return r;
 }
-// mid/side inverse (decoder.rs:75-89), i32 -> f32 (audio_constants.rs:24-26), interleaved store.
+// mid/side inverse (decoder.rs:75-89), i32 -> f32 (audio_constants.rs:24-26).
 // `o` is the neighbour lane's sample (the other channel of a stereo frame).
-__device__ __forceinline__ void emit_pair(const Lane &L, uint32_t i, int32_t s, int32_t o) {
+__device__ __forceinline__ float to_output(const Lane &L, int32_t s, int32_t o) {
     int32_t v = s;
     if (L.ms) {
         const uint32_t m = (uint32_t)(L.odd ? o : s), d = (uint32_t)(L.odd ? s : o);
         v = (int32_t)(L.odd ? m - d : m + d) / 2;
     }
-    if (i < L.n) L.outp[(size_t)i * L.stride] = __fmul_rn(__int2float_rn(v), 1.0f / 32767.0f);
+    return __fmul_rn(__int2float_rn(v), 1.0f / 32767.0f);
 }
-__device__ __forceinline__ void emit(const Lane &L, uint32_t i, int32_t s) { emit_pair(L, i, s, __shfl_xor_sync(FULL, s, 1)); }
+__device__ __forceinline__ void store_if(float *p, float v, bool on) {     // predicated store: no branch in the sample loop
+    asm volatile("{\n .reg .pred q;\n setp.ne.u32 q, %2, 0;\n @q st.global.f32 [%0], %1;\n}" :: "l"(p), "f"(v), "r"((uint32_t)on) : "memory");
+}
+__device__ __forceinline__ void emit(const Lane &L, uint32_t i, int32_t s) {
+    store_if(L.outp + (size_t)i * L.stride, to_output(L, s, __shfl_xor_sync(FULL, s, 1)), i < L.n);
+}
 
 // Steady state for Rice-coded lanes with predictors of at most ORD taps: history newest-first in ORD registers,
 // GROUP samples per trip (one ring top-up per trip).  The per-sample loop stays rolled so that there is one copy
-// of the bit reader; the neighbour shuffle of sample i is consumed while sample i + 1 is decoded.
+// of the bit reader; the neighbour shuffle of sample i is consumed while sample i + 1 is decoded (the first trip
+// re-emits sample i - 1, which the generic step already wrote).
 template <int ORD>
 __device__ __forceinline__ uint32_t synth_blocks(Lane &L, uint32_t i, uint32_t nmax, const int32_t (&c12)[12], int32_t (&hist)[12]) {
-    if (i + GROUP > nmax) return i;
+    if (i == 0 || i + GROUP > nmax) return i;
     int32_t c[ORD], h[ORD];
     #pragma unroll
     for (int j = 0; j < ORD; j++) { c[j] = c12[j]; h[j] = hist[j]; }
     const int sh = L.shift;
-    int32_t s_prev = 0, o_prev = 0;
-    bool have_prev = false;
+    int32_t s_prev = hist[0], o_prev = __shfl_xor_sync(FULL, hist[0], 1);
+    float *op = L.outp + (size_t)(i - 1) * L.stride;       // where sample i - 1 goes
+    uint32_t left = L.n >= i ? L.n - i + 1 : 0;            // samples of this lane from i - 1 on
     #pragma unroll 1
     for (; i + GROUP <= nmax; i += GROUP) {
         topup(L.ring, L.lane, L.bits);
         #pragma unroll 1
         for (int t = 0; t < GROUP; t++) {
             const int32_t r = rice_next(L.ring, L.lane, L.bits, L.k);
-            long long acc = 0;
+            long long a0 = 0, a1 = 0;                      // two chains; the newest sample enters last
             #pragma unroll
-            for (int j = ORD - 1; j >= 0; j--) acc += (long long)c[j] * (long long)h[j];    // newest sample last: shortest carried chain
-            const int32_t s = (int32_t)((uint32_t)(int32_t)(acc >> sh) + (uint32_t)r);
+            for (int j = ORD - 1; j >= 0; j--) {
+                if (j & 1) a1 += (long long)c[j] * (long long)h[j];
+                else a0 += (long long)c[j] * (long long)h[j];
+            }
+            const int32_t s = (int32_t)((uint32_t)(int32_t)((a0 + a1) >> sh) + (uint32_t)r);
             #pragma unroll
             for (int j = ORD - 1; j > 0; j--) h[j] = h[j - 1];
             h[0] = s;
-            if (have_prev) emit_pair(L, i + t - 1, s_prev, o_prev);
-            s_prev = s; o_prev = __shfl_xor_sync(FULL, s, 1); have_prev = true;
+            store_if(op, to_output(L, s_prev, o_prev), left != 0);
+            op += L.stride; left -= left ? 1u : 0u;
+            s_prev = s; o_prev = __shfl_xor_sync(FULL, s, 1);
         }
     }
-    emit_pair(L, i - 1, s_prev, o_prev);
+    store_if(op, to_output(L, s_prev, o_prev), left != 0);
     #pragma unroll
     for (int j = 0; j < ORD; j++) hist[j] = h[j];
     return i;
