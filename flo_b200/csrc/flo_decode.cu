@@ -106,10 +106,15 @@ struct BitIn {
     uint32_t npend;
     uint32_t wr, rd;                  // ring word counters: next word to store / word held in nxt
     unsigned long long end_off;       // payload end, as a byte offset from the aligned base of the stream
-    uint32_t nxt;                     // ring[rd], loaded ahead
+    uint32_t nxt;                     // ring[rd] as stored (little-endian), loaded ahead; byte-swapped when appended
     unsigned long long buf;           // MSB-aligned window
     int nb;                           // bits in the window
 };
+// The ring is addressed in the shared window directly (rs = this lane's column, 128 bytes between its words).
+__device__ __forceinline__ uint32_t lds32(uint32_t a) { uint32_t v; asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(a)); return v; }
+__device__ __forceinline__ void sts32(uint32_t a, uint32_t v) { asm volatile("st.shared.u32 [%0], %1;" :: "r"(a), "r"(v)); }
+__device__ __forceinline__ uint32_t ring_at(uint32_t rs, uint32_t idx) { return lds32(rs + ((idx & (RING - 1)) << 7)); }
+__device__ __forceinline__ uint32_t be(uint32_t raw) { return __byte_perm(raw, 0u, 0x0123); }
 // Past the end of the image the address is clamped (the bytes are masked off in put_vec anyway): nothing may
 // depend on the loaded registers until the next top-up stores them.
 __device__ __forceinline__ uint4 ldv(const uint4 *p, const uint4 *end) { return __ldg(p < end ? p : end - 1); }
@@ -120,34 +125,31 @@ __device__ __forceinline__ uint32_t le_masked(uint32_t raw, unsigned long long p
     if (pos + 4 <= end_off) return raw;
     return pos >= end_off ? 0u : (raw & ~(0xFFFFFFFFu << (8u * (uint32_t)(end_off - pos))));
 }
-__device__ __forceinline__ void put_vec(uint32_t *ring, uint32_t lane, BitIn &b, const uint4 &v) {
-    uint32_t *slot = ring + ((b.wr & (RING - 1)) << 5) + lane;        // wr is a multiple of 4: the four slots do not wrap
+__device__ __forceinline__ void put_vec(uint32_t rs, BitIn &b, const uint4 &v) {
+    const uint32_t slot = rs + ((b.wr & (RING - 1)) << 7);  // wr is a multiple of 4: the four slots do not wrap
     const unsigned long long pos = 4ull * b.wr;
     if (pos + 16 <= b.end_off) {
-        slot[0] = v.x; slot[32] = v.y; slot[64] = v.z; slot[96] = v.w;
+        sts32(slot, v.x); sts32(slot + 128, v.y); sts32(slot + 256, v.z); sts32(slot + 384, v.w);
     } else {                                               // the payload ends inside this vector: later bytes read as 0
-        slot[0] = le_masked(v.x, pos, b.end_off); slot[32] = le_masked(v.y, pos + 4, b.end_off);
-        slot[64] = le_masked(v.z, pos + 8, b.end_off); slot[96] = le_masked(v.w, pos + 12, b.end_off);
+        sts32(slot, le_masked(v.x, pos, b.end_off)); sts32(slot + 128, le_masked(v.y, pos + 4, b.end_off));
+        sts32(slot + 256, le_masked(v.z, pos + 8, b.end_off)); sts32(slot + 384, le_masked(v.w, pos + 12, b.end_off));
     }
     b.wr += 4;
 }
-__device__ __forceinline__ uint32_t ring_word(const uint32_t *ring, uint32_t lane, uint32_t idx) {
-    return __byte_perm(ring[((idx & (RING - 1)) << 5) + lane], 0u, 0x0123);             // big-endian: MSB first
-}
-__device__ __forceinline__ void topup_once(uint32_t *ring, uint32_t lane, BitIn &b) {
-    if (b.npend >= 1) put_vec(ring, lane, b, b.p0);
-    if (b.npend == 2) put_vec(ring, lane, b, b.p1);
+__device__ __forceinline__ void topup_once(uint32_t rs, BitIn &b) {
+    if (b.npend >= 1) put_vec(rs, b, b.p0);
+    if (b.npend == 2) put_vec(rs, b, b.p1);
     b.npend = 0;
     const uint32_t room = RING - (b.wr - b.rd);
     if (room >= 4) { b.p0 = ldv(b.gp, b.vend); b.gp++; b.npend = 1; }
     if (room >= 8) { b.p1 = ldv(b.gp, b.vend); b.gp++; b.npend = 2; }
 }
 // Warp-uniform.  Afterwards every lane holds at least 2 * GROUP words, so the fast path cannot run dry before the next call.
-__device__ __forceinline__ void topup(uint32_t *ring, uint32_t lane, BitIn &b) {
-    do topup_once(ring, lane, b);
+__device__ __forceinline__ void topup(uint32_t rs, BitIn &b) {
+    do topup_once(rs, b);
     while (__any_sync(FULL, b.wr - b.rd < 2 * GROUP));      // rare second trip: waits for the loads just issued
 }
-__device__ __forceinline__ void bits_init(uint32_t *ring, uint32_t lane, BitIn &b, const uint8_t *file, unsigned long long len,
+__device__ __forceinline__ void bits_init(uint32_t rs, BitIn &b, const uint8_t *file, unsigned long long len,
                                           unsigned long long start, uint32_t nbytes) {
     const uintptr_t a = (uintptr_t)(file + start), a0 = a & ~(uintptr_t)15;
     const uint32_t sk = (uint32_t)(a - a0);
@@ -156,33 +158,33 @@ __device__ __forceinline__ void bits_init(uint32_t *ring, uint32_t lane, BitIn &
     b.end_off = (unsigned long long)sk + nbytes;
     b.npend = 0; b.wr = 0; b.rd = 0;
     b.p0 = b.p1 = make_uint4(0u, 0u, 0u, 0u);
-    topup(ring, lane, b);
+    topup(rs, b);
     b.rd = sk >> 2;                                        // the payload starts sk bytes into the first vector
     const uint32_t sb = sk & 3u;
-    const uint32_t w = ring_word(ring, lane, b.rd);
+    const uint32_t w = be(ring_at(rs, b.rd));
     b.rd++;
     b.buf = sb ? (unsigned long long)(w << (8u * sb)) << 32 : (unsigned long long)w << 32;
     b.nb = 32 - 8 * (int)sb;
-    b.nxt = ring_word(ring, lane, b.rd);
+    b.nxt = ring_at(rs, b.rd);
 }
 // lane-private (divergent) fill: at least `want` words on hand; fetches synchronously when the ring is dry
-__device__ __forceinline__ void lane_fill(uint32_t *ring, uint32_t lane, BitIn &b, int want) {
+__device__ __forceinline__ void lane_fill(uint32_t rs, BitIn &b, int want) {
     while ((int)(b.wr - b.rd) < want) {
-        if (b.npend) { put_vec(ring, lane, b, b.p0); if (b.npend == 2) put_vec(ring, lane, b, b.p1); b.npend = 0; }
+        if (b.npend) { put_vec(rs, b, b.p0); if (b.npend == 2) put_vec(rs, b, b.p1); b.npend = 0; }
         else { b.p0 = ldv(b.gp, b.vend); b.gp++; b.npend = 1; }
     }
 }
-__device__ __forceinline__ void refill_slow(uint32_t *ring, uint32_t lane, BitIn &b) {
+__device__ __forceinline__ void refill_slow(uint32_t rs, BitIn &b) {
     if (b.nb > 32) return;
-    b.buf |= (unsigned long long)b.nxt << (32 - b.nb); b.nb += 32; b.rd++;
-    b.nxt = ring_word(ring, lane, b.rd);
+    b.buf |= (unsigned long long)be(b.nxt) << (32 - b.nb); b.nb += 32; b.rd++;
+    b.nxt = ring_at(rs, b.rd);
 }
 // decode_i32's loop body (rice.rs:127-155): unary quotient (ones, capped at 256 reads), k-bit remainder, zigzag.
 // Rare path: the code does not fit the bits on hand (long unary run, large k).  One code takes at most
 // 256 + 1 + 31 bits = 9 words; with 20 on hand at entry the rest of the group still pops without checking.
-__device__ __forceinline__ uint32_t rice_slow(uint32_t *ring, uint32_t lane, BitIn &b, uint32_t k) {
-    lane_fill(ring, lane, b, GROUP + 12);
-    b.nxt = ring_word(ring, lane, b.rd);
+__device__ __forceinline__ uint32_t rice_slow(uint32_t rs, BitIn &b, uint32_t k) {
+    lane_fill(rs, b, GROUP + 12);
+    b.nxt = ring_at(rs, b.rd);
     uint32_t q = 0;
     for (;;) {
         int run = __clzll((long long)~b.buf);
@@ -196,23 +198,25 @@ __device__ __forceinline__ uint32_t rice_slow(uint32_t *ring, uint32_t lane, Bit
         q += (uint32_t)run;
         if (!more) { b.buf = (b.buf << run) << 1; b.nb -= run + 1; break; }
         b.buf = 0; b.nb = 0;
-        refill_slow(ring, lane, b);
+        refill_slow(rs, b);
     }
-    refill_slow(ring, lane, b);
+    refill_slow(rs, b);
     uint32_t r = 0;
     if (k) { r = (uint32_t)(b.buf >> (64 - k)); b.buf <<= k; b.nb -= (int)k; }
     return (q << k) | r;
 }
 // Common path, branch-free up to the fit test: append the word on hand when the window is half empty, count the
 // leading ones of the top word, cut the k remainder bits out with funnel shifts.
-__device__ __forceinline__ int32_t rice_next(uint32_t *ring, uint32_t lane, BitIn &b, uint32_t k) {
-    const bool need = b.nb <= 32;                          // then the low word of the window is empty
-    const uint32_t hi0 = (uint32_t)(b.buf >> 32);
-    const uint32_t hi = need ? (hi0 | __funnelshift_rc(b.nxt, 0u, (uint32_t)b.nb)) : hi0;
-    const uint32_t lo = need ? __funnelshift_lc(0u, b.nxt, 32u - (uint32_t)b.nb) : (uint32_t)b.buf;
-    b.nb += need ? 32 : 0;
-    b.rd += need ? 1u : 0u;
-    b.nxt = ring_word(ring, lane, b.rd);       // not needed before the next sample
+__device__ __forceinline__ int32_t rice_next(uint32_t rs, BitIn &b, uint32_t k) {
+    uint32_t hi = (uint32_t)(b.buf >> 32), lo = (uint32_t)b.buf;
+    if (b.nb <= 32) {                                      // the low word of the window is empty (predicated, not a branch)
+        const uint32_t w = be(b.nxt);
+        hi |= __funnelshift_rc(w, 0u, (uint32_t)b.nb);
+        lo = __funnelshift_lc(0u, w, 32u - (uint32_t)b.nb);
+        b.nb += 32;
+        b.rd++;
+    }
+    b.nxt = ring_at(rs, b.rd);                             // not needed before the next sample
     const int run = __clz((int)~hi);                       // leading ones (32: the run leaves the top word)
     const int used = run + 1 + (int)k;
     b.buf = ((unsigned long long)hi << 32) | lo;
@@ -222,7 +226,7 @@ __device__ __forceinline__ int32_t rice_next(uint32_t *ring, uint32_t lane, BitI
         u = ((uint32_t)run << k) | __funnelshift_rc(t, 0u, 32u - k);
         b.buf <<= used; b.nb -= used;                      // used <= 63
     } else {
-        u = rice_slow(ring, lane, b, k);
+        u = rice_slow(rs, b, k);
     }
     return (int32_t)(u >> 1) ^ -(int32_t)(u & 1u);
 }
@@ -233,7 +237,8 @@ enum { M_ZERO = 0, M_RICE = 1, M_PCM = 2 };
 
 struct Lane {
     BitIn bits;
-    uint32_t *ring; uint32_t lane;
+    uint32_t rs;                      // this lane's ring column (shared-window address)
+    uint32_t msa, msb, mshift;        // output = (s * msa + neighbour * msb) / 2^mshift, truncating (mid/side inverse)
     bool any_pcm;                     // warp-uniform: some lane reads raw PCM
     const uint8_t *pcm; uint32_t pcm_bytes;
     float *outp; uint32_t stride;
@@ -244,7 +249,7 @@ struct Lane {
 };
 
 __device__ __forceinline__ int32_t next_residual(Lane &L, uint32_t i) {
-    int32_t r = rice_next(L.ring, L.lane, L.bits, L.k);
+    int32_t r = rice_next(L.rs, L.bits, L.k);
     if (L.src == M_PCM) {                                  // decoder.rs:132-143
         r = 0;
         if (2ull * i + 1 < L.pcm_bytes) r = (int16_t)((uint16_t)__ldg(L.pcm + 2ull * i) | ((uint16_t)__ldg(L.pcm + 2ull * i + 1) << 8));
@@ -252,13 +257,12 @@ __device__ __forceinline__ int32_t next_residual(Lane &L, uint32_t i) {
     return r;
 }
 // mid/side inverse (decoder.rs:75-89), i32 -> f32 (audio_constants.rs:24-26).
-// `o` is the neighbour lane's sample (the other channel of a stereo frame).
+// `o` is the neighbour lane's sample (the other channel of a stereo frame): L = (m + s) / 2 on the even lane,
+// R = (m - s) / 2 on the odd one, `/` truncating toward zero, all in wrapping 32-bit arithmetic; other frames
+// pass s through.  One multiply-add form for all three so that the sample loop has no selects.
 __device__ __forceinline__ float to_output(const Lane &L, int32_t s, int32_t o) {
-    int32_t v = s;
-    if (L.ms) {
-        const uint32_t m = (uint32_t)(L.odd ? o : s), d = (uint32_t)(L.odd ? s : o);
-        v = (int32_t)(L.odd ? m - d : m + d) / 2;
-    }
+    const uint32_t t = (uint32_t)s * L.msa + (uint32_t)o * L.msb;
+    const int32_t v = (int32_t)(t + ((t >> 31) & L.mshift)) >> L.mshift;
     return __fmul_rn(__int2float_rn(v), 1.0f / 32767.0f);
 }
 __device__ __forceinline__ void store_if(float *p, float v, bool on) {     // predicated store: no branch in the sample loop
@@ -281,13 +285,13 @@ __device__ __forceinline__ uint32_t synth_blocks(Lane &L, uint32_t i, uint32_t n
     const int sh = L.shift;
     int32_t s_prev = hist[0], o_prev = __shfl_xor_sync(FULL, hist[0], 1);
     float *op = L.outp + (size_t)(i - 1) * L.stride;       // where sample i - 1 goes
-    uint32_t left = L.n >= i ? L.n - i + 1 : 0;            // samples of this lane from i - 1 on
+    const uint32_t n = L.n;
     #pragma unroll 1
     for (; i + GROUP <= nmax; i += GROUP) {
-        topup(L.ring, L.lane, L.bits);
-        #pragma unroll 1
+        topup(L.rs, L.bits);
+        #pragma unroll 2
         for (int t = 0; t < GROUP; t++) {
-            const int32_t r = rice_next(L.ring, L.lane, L.bits, L.k);
+            const int32_t r = rice_next(L.rs, L.bits, L.k);
             long long a0 = 0, a1 = 0;                      // two chains; the newest sample enters last
             #pragma unroll
             for (int j = ORD - 1; j >= 0; j--) {
@@ -298,12 +302,12 @@ __device__ __forceinline__ uint32_t synth_blocks(Lane &L, uint32_t i, uint32_t n
             #pragma unroll
             for (int j = ORD - 1; j > 0; j--) h[j] = h[j - 1];
             h[0] = s;
-            store_if(op, to_output(L, s_prev, o_prev), left != 0);
-            op += L.stride; left -= left ? 1u : 0u;
+            store_if(op, to_output(L, s_prev, o_prev), i + t <= n);        // sample i + t - 1
+            op += L.stride;
             s_prev = s; o_prev = __shfl_xor_sync(FULL, s, 1);
         }
     }
-    store_if(op, to_output(L, s_prev, o_prev), left != 0);
+    store_if(op, to_output(L, s_prev, o_prev), i <= n);
     #pragma unroll
     for (int j = 0; j < ORD; j++) hist[j] = h[j];
     return i;
@@ -311,7 +315,7 @@ __device__ __forceinline__ uint32_t synth_blocks(Lane &L, uint32_t i, uint32_t n
 
 // Generic step with the history newest-first in hist[]: warm-up rules (decoder.rs:163-165, 199-259) and block tails.
 __device__ __forceinline__ void synth_step(Lane &L, uint32_t i, const int32_t (&c12)[12], int32_t (&hist)[12]) {
-    topup(L.ring, L.lane, L.bits);
+    topup(L.rs, L.bits);
     const int32_t r = next_residual(L, i);
     int32_t pred = 0;
     if (i >= (uint32_t)L.order) {
@@ -415,9 +419,12 @@ __global__ void __launch_bounds__(32) k_dec_units(DecodeParams p) {
         }
         // Silence / reserved types: zeros (reader.rs:180, 246)
     }
-    L.ring = ring; L.lane = lane;
+    L.rs = (uint32_t)__cvta_generic_to_shared(ring) + 4u * lane;
+    L.msa = L.ms ? (L.odd ? 0xFFFFFFFFu : 1u) : 1u;
+    L.msb = L.ms ? 1u : 0u;
+    L.mshift = L.ms ? 1u : 0u;
     L.any_pcm = __any_sync(FULL, L.src == M_PCM);
-    bits_init(ring, lane, L.bits, f, p.len, L.src == M_RICE ? rpos : 0ull, L.src == M_RICE ? rbytes : 0u);
+    bits_init(L.rs, L.bits, f, p.len, L.src == M_RICE ? rpos : 0ull, L.src == M_RICE ? rbytes : 0u);
 
     const uint32_t nmax = __reduce_max_sync(FULL, L.n);
     const int omax = (int)__reduce_max_sync(FULL, (uint32_t)L.order);
