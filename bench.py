@@ -296,6 +296,21 @@ def main() -> int:
         extras["pcm16_entry"] = {"kernel_ms": min(ts), "same_bytes_as_f32_entry": int(l2.sum()) == out_bytes,
                                  "pct_of_hbm_peak": 100.0 * (2.0 * total_inter + float(l2.sum())) / (min(ts) * 1e-3) / 1e9 / peak}
 
+        # companion row N2: decode the file just written, device-resident, and check the round trip
+        d_dec = torch.empty(total_inter, dtype=torch.float32, device=dev)
+        ts = []
+        for _ in range(3):
+            n_dec, _info = ctx.decode_device(d_out.data_ptr() + int(o2[0]), int(l2[0]), d_dec.data_ptr(), d_dec.numel())
+            ts.append(ctx.last_timing())
+        q = torch.trunc(torch.clamp(f32_tracks[0] * 32767.0, -32767.0, 32767.0)) * torch.tensor(1.0 / 32767.0, dtype=torch.float32, device=dev)
+        k_dec = min(t["encode_ms"] for t in ts)
+        extras["decode"] = {"kernel": "k_dec_units", "kernel_ms": k_dec, "device_pass_ms": min(t["device_ms"] for t in ts),
+                            "launches": ts[-1]["launches"], "round_trip_exact": bool(n_dec == total_inter and torch.equal(d_dec, q)),
+                            "pct_of_hbm_peak": 100.0 * (4.0 * total_inter + float(l2[0])) / (k_dec * 1e-3) / 1e9 / peak,
+                            "note": "flo_decode_device on the level-5 file of the same stream; latency-bound (one lane per "
+                                    "channel of a frame), see DESIGN.md section 9.2"}
+        del d_dec, q
+
     # e2e: host buffers through the reference-facing C-ABI call (H2D + D2H inside the timed region)
     e2e = None
     if not args.no_e2e:
