@@ -5,6 +5,7 @@ Drop-in for `libflo_audio::Encoder::{new, with_compression, encode}` only; see D
 from ._lib import FMT_F32, FMT_PCM16, FloError, SO_PATH
 from .encoder import Context, Decoder, Encoder, TrackSpec, default_context, encode_batch
 from . import reflo
+from .streaming import EncodedFrame, StreamingEncoder
 
 __all__ = ["Encoder", "Decoder", "Context", "TrackSpec", "encode_batch", "default_context", "FloError", "FMT_F32", "FMT_PCM16",
-           "SO_PATH", "reflo"]
+           "SO_PATH", "reflo", "StreamingEncoder", "EncodedFrame"]

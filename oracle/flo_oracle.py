@@ -331,3 +331,110 @@ def decode_i32(data: bytes) -> np.ndarray:
     out = np.ctypeslib.as_array(p, shape=(max(n.value, 1),))[:n.value].copy()
     lib().flo_ref_free(p)
     return out
+
+
+# ---- streaming/encoder.rs ------------------------------------------------------------------------------
+def _f64_as_u32(v: float) -> int:
+    if v != v or v <= 0.0:
+        return 0
+    return min(int(v), 0xFFFFFFFF)
+
+
+class StreamingEncoderRef:
+    """Restatement of StreamingEncoder (libflo/src/streaming/encoder.rs:5-257) over this oracle's Encoder and
+    Reader.  Test infrastructure only.  Parity unpinned: the reference ships no streaming bitstreams; the
+    restatement follows the source line by line and is cross-checked through the oracle's own reader."""
+
+    def __init__(self, sample_rate: int, channels: int, bit_depth: int):
+        self.sample_rate, self.channels, self.bit_depth = sample_rate, channels, bit_depth
+        self.level = 5                                                        # encoder.rs:39
+        self.samples_per_frame = sample_rate                                  # encoder.rs:34
+        self.buf: List[float] = []
+        self.pending: List[dict] = []
+        self.total_samples = 0
+        self.frame_index = 0
+
+    def with_compression(self, level: int) -> "StreamingEncoderRef":          # encoder.rs:51-56
+        self.level = min(level, 9)
+        return self
+
+    def pending_samples(self) -> int:
+        return len(self.buf) // self.channels
+
+    def pending_frames(self) -> int:
+        return len(self.pending)
+
+    def _serialize_channel(self, ch: "ChannelInfo", body: bytes, ftype: int) -> bytes:   # encoder.rs:243-257
+        res = body[len(body) - ch.residual_bytes:] if ch.residual_bytes else b""
+        if ftype == 0:
+            return b""
+        if ftype in (254, 253):
+            return body[:ch.residual_bytes]
+        out = bytes([ch.k])
+        for c in ch.coeffs:
+            out += int(c).to_bytes(4, "little", signed=True)
+        return out + res
+
+    def _encode_frame_data(self, samples: np.ndarray) -> bytes:               # encoder.rs:216-241
+        f = FloFile(encode(samples, self.sample_rate, self.channels, self.bit_depth, self.level, b""))
+        if not f.frames:
+            raise ValueError("No frames encoded")
+        fr = f.frames[0]
+        raw = f.frame_bytes(0)
+        out = bytes([fr.frame_type]) + int(fr.frame_samples).to_bytes(4, "little") + bytes([fr.flags])
+        pos = 6
+        for ch in fr.channels:
+            size = int.from_bytes(raw[pos:pos + 4], "little")
+            body = raw[pos + 4:pos + 4 + size]
+            pos += 4 + size
+            cd = self._serialize_channel(ch, body, fr.frame_type)
+            out += len(cd).to_bytes(4, "little") + cd
+        return out
+
+    def push_samples(self, samples) -> None:                                  # encoder.rs:71-75, 189-213
+        self.buf.extend(np.asarray(samples, np.float32).reshape(-1).tolist())
+        frame_samples = self.samples_per_frame * self.channels
+        while len(self.buf) >= frame_samples:
+            frame = np.asarray(self.buf[:frame_samples], np.float32)
+            del self.buf[:frame_samples]
+            ts = _f64_as_u32(self.total_samples / float(self.sample_rate) * 1000.0)
+            self.pending.append({"index": self.frame_index, "timestamp_ms": ts, "data": self._encode_frame_data(frame),
+                                 "samples": self.samples_per_frame})
+            self.total_samples += self.samples_per_frame
+            self.frame_index += 1
+
+    def next_frame(self):                                                     # encoder.rs:78-84
+        return self.pending.pop(0) if self.pending else None
+
+    def flush(self):                                                          # encoder.rs:87-110
+        if not self.buf:
+            return None
+        per = len(self.buf) // self.channels
+        ts = _f64_as_u32(self.total_samples / float(self.sample_rate) * 1000.0)
+        fr = {"index": self.frame_index, "timestamp_ms": ts, "data": self._encode_frame_data(np.asarray(self.buf, np.float32)),
+              "samples": per}
+        self.total_samples += per
+        self.frame_index += 1
+        self.buf = []
+        return fr
+
+    def finalize(self, metadata: bytes = b"") -> bytes:                       # encoder.rs:113-183
+        fr = self.flush()
+        if fr is not None:
+            self.pending.append(fr)
+        toc = len(self.pending).to_bytes(4, "little")
+        off = 0
+        for f in self.pending:
+            toc += f["index"].to_bytes(4, "little") + off.to_bytes(8, "little") + len(f["data"]).to_bytes(4, "little") \
+                + f["timestamp_ms"].to_bytes(4, "little")
+            off += len(f["data"])
+        data = b"".join(f["data"] for f in self.pending)
+        total = sum(f["samples"] for f in self.pending)
+        out = b"FLO!" + bytes([1, 2]) + (0).to_bytes(2, "little") + self.sample_rate.to_bytes(4, "little")
+        out += bytes([self.channels, self.bit_depth]) + total.to_bytes(8, "little") + bytes([self.level, 0, 0, 0])
+        out += crc32(data).to_bytes(4, "little")
+        for v in (66, len(toc), len(data), 0, len(metadata)):
+            out += v.to_bytes(8, "little")
+        out += toc + data + bytes(metadata)
+        self.pending = []
+        return out
