@@ -111,8 +111,8 @@ struct BitIn {
     int nb;                           // bits in the window
 };
 // The ring is addressed in the shared window directly (rs = this lane's column, 128 bytes between its words).
-__device__ __forceinline__ uint32_t lds32(uint32_t a) { uint32_t v; asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(a)); return v; }
-__device__ __forceinline__ void sts32(uint32_t a, uint32_t v) { asm volatile("st.shared.u32 [%0], %1;" :: "r"(a), "r"(v)); }
+__device__ __forceinline__ uint32_t lds32(uint32_t a) { uint32_t v; asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(a) : "memory"); return v; }
+__device__ __forceinline__ void sts32(uint32_t a, uint32_t v) { asm volatile("st.shared.u32 [%0], %1;" :: "r"(a), "r"(v) : "memory"); }
 __device__ __forceinline__ uint32_t ring_at(uint32_t rs, uint32_t idx) { return lds32(rs + ((idx & (RING - 1)) << 7)); }
 __device__ __forceinline__ uint32_t be(uint32_t raw) { return __byte_perm(raw, 0u, 0x0123); }
 // Past the end of the image the address is clamped (the bytes are masked off in put_vec anyway): nothing may
@@ -239,7 +239,6 @@ struct Lane {
     BitIn bits;
     uint32_t rs;                      // this lane's ring column (shared-window address)
     uint32_t msa, msb, mshift;        // output = (s * msa + neighbour * msb) / 2^mshift, truncating (mid/side inverse)
-    bool any_pcm;                     // warp-uniform: some lane reads raw PCM
     const uint8_t *pcm; uint32_t pcm_bytes;
     float *outp; uint32_t stride;
     uint32_t n, k;
@@ -272,51 +271,36 @@ __device__ __forceinline__ void emit(const Lane &L, uint32_t i, int32_t s) {
     store_if(L.outp + (size_t)i * L.stride, to_output(L, s, __shfl_xor_sync(FULL, s, 1)), i < L.n);
 }
 
-// Steady state for Rice-coded lanes with predictors of at most ORD taps: history newest-first in ORD registers,
-// GROUP samples per trip (one ring top-up per trip).  The per-sample loop stays rolled so that there is one copy
-// of the bit reader; the neighbour shuffle of sample i is consumed while sample i + 1 is decoded (the first trip
-// re-emits sample i - 1, which the generic step already wrote).
-template <int ORD>
-__device__ __forceinline__ uint32_t synth_blocks(Lane &L, uint32_t i, uint32_t nmax, const int32_t (&c12)[12], int32_t (&hist)[12]) {
-    if (i == 0 || i + GROUP > nmax) return i;
-    int32_t c[ORD], h[ORD];
-    #pragma unroll
-    for (int j = 0; j < ORD; j++) { c[j] = c12[j]; h[j] = hist[j]; }
-    const int sh = L.shift;
-    int32_t s_prev = hist[0], o_prev = __shfl_xor_sync(FULL, hist[0], 1);
-    float *op = L.outp + (size_t)(i - 1) * L.stride;       // where sample i - 1 goes
-    const uint32_t n = L.n;
-    #pragma unroll 1
-    for (; i + GROUP <= nmax; i += GROUP) {
-        topup(L.rs, L.bits);
-        #pragma unroll 2
-        for (int t = 0; t < GROUP; t++) {
-            const int32_t r = rice_next(L.rs, L.bits, L.k);
-            long long a0 = 0, a1 = 0;                      // two chains; the newest sample enters last
-            #pragma unroll
-            for (int j = ORD - 1; j >= 0; j--) {
-                if (j & 1) a1 += (long long)c[j] * (long long)h[j];
-                else a0 += (long long)c[j] * (long long)h[j];
-            }
-            const int32_t s = (int32_t)((uint32_t)(int32_t)((a0 + a1) >> sh) + (uint32_t)r);
-            #pragma unroll
-            for (int j = ORD - 1; j > 0; j--) h[j] = h[j - 1];
-            h[0] = s;
-            store_if(op, to_output(L, s_prev, o_prev), i + t <= n);        // sample i + t - 1
-            op += L.stride;
-            s_prev = s; o_prev = __shfl_xor_sync(FULL, s, 1);
-        }
-    }
-    store_if(op, to_output(L, s_prev, o_prev), i <= n);
-    #pragma unroll
-    for (int j = 0; j < ORD; j++) hist[j] = h[j];
-    return i;
-}
+// ---- predictor side ----
+constexpr int BLK = 16;               // samples handed from the bit-reading warp to the predictor warp at a time
 
-// Generic step with the history newest-first in hist[]: warm-up rules (decoder.rs:163-165, 199-259) and block tails.
-__device__ __forceinline__ void synth_step(Lane &L, uint32_t i, const int32_t (&c12)[12], int32_t (&hist)[12]) {
-    topup(L.rs, L.bits);
-    const int32_t r = next_residual(L, i);
+template <int ORD>
+__device__ __forceinline__ int32_t fir(const int32_t (&c)[ORD], const int32_t (&h)[ORD], int sh, int32_t r) {
+    long long a0 = 0, a1 = 0;                              // two chains; the newest sample enters last
+    #pragma unroll
+    for (int j = ORD - 1; j >= 0; j--) {
+        if (j & 1) a1 += (long long)c[j] * (long long)h[j];
+        else a0 += (long long)c[j] * (long long)h[j];
+    }
+    return (int32_t)((uint32_t)(int32_t)((a0 + a1) >> sh) + (uint32_t)r);
+}
+// Steady state (sample index >= 12 >= order): reconstruct_lpc_int's loop (decoder.rs:169-179) / the fixed
+// recurrences (decoder.rs:199-259) as one FIR of at most ORD taps.  Fully unrolled over the block, so the history
+// is renamed instead of moved and the shuffle / convert / store of sample t overlap the filter step of t + 1.
+template <int ORD>
+__device__ __forceinline__ void consume_block(const Lane &L, uint32_t res, uint32_t i0, const int32_t (&c)[ORD], int32_t (&h)[ORD], float *&op) {
+    #pragma unroll
+    for (int t = 0; t < BLK; t++) {
+        const int32_t s = fir<ORD>(c, h, L.shift, (int32_t)lds32(res + 128u * t));
+        #pragma unroll
+        for (int j = ORD - 1; j > 0; j--) h[j] = h[j - 1];
+        h[0] = s;
+        store_if(op, to_output(L, s, __shfl_xor_sync(FULL, s, 1)), i0 + t < L.n);
+        op += L.stride;
+    }
+}
+// Generic step with the history newest-first in hist[]: warm-up rules (decoder.rs:163-165, 199-259).
+__device__ __forceinline__ void synth_apply(const Lane &L, uint32_t i, int32_t r, const int32_t (&c12)[12], int32_t (&hist)[12]) {
     int32_t pred = 0;
     if (i >= (uint32_t)L.order) {
         long long acc = 0;
@@ -335,23 +319,57 @@ __device__ __forceinline__ void synth_step(Lane &L, uint32_t i, const int32_t (&
     hist[0] = s;
     emit(L, i, s);
 }
+// Predictor warp: block b of residuals is consumed while the bit-reading warp produces block b + 1.
+template <int ORD>
+__device__ __forceinline__ void consumer_loop(const Lane &L, uint32_t res0, uint32_t nblk, const int32_t (&c12)[12], int32_t (&hist)[12]) {
+    int32_t c[ORD], h[ORD];
+    #pragma unroll
+    for (int j = 0; j < ORD; j++) { c[j] = c12[j]; h[j] = 0; }
+    float *op = L.outp + (size_t)BLK * L.stride;
+    for (uint32_t ph = 0; ph <= nblk; ph++) {
+        if (ph == 1) {                                     // first block: warm-up rules, generic taps
+            #pragma unroll 1
+            for (int t = 0; t < BLK; t++) synth_apply(L, (uint32_t)t, (int32_t)lds32(res0 + 128u * t), c12, hist);
+            #pragma unroll
+            for (int j = 0; j < ORD; j++) h[j] = hist[j];
+        } else if (ph > 1) {
+            consume_block<ORD>(L, res0 + (((ph - 1) & 1u) ? 128u * BLK : 0u), (ph - 1) * BLK, c, h, op);
+        }
+        __syncthreads();
+    }
+}
+// Bit-reading warp: residual i of every lane -> res[block parity][i % BLK][lane].
+__device__ __forceinline__ void producer_loop(Lane &L, uint32_t res0, uint32_t nblk, bool any_pcm) {
+    for (uint32_t ph = 0; ph <= nblk; ph++) {
+        if (ph < nblk) {
+            const uint32_t res = res0 + ((ph & 1u) ? 128u * BLK : 0u);
+            #pragma unroll 1
+            for (int g = 0; g < BLK; g += GROUP) {
+                topup(L.rs, L.bits);
+                if (!any_pcm) {
+                    #pragma unroll 2
+                    for (int t = 0; t < GROUP; t++) sts32(res + 128u * (g + t), (uint32_t)rice_next(L.rs, L.bits, L.k));
+                } else {                                   // raw PCM lanes (rare): the generic source for the whole warp
+                    #pragma unroll 1
+                    for (int t = 0; t < GROUP; t++) sts32(res + 128u * (g + t), (uint32_t)next_residual(L, ph * BLK + g + t));
+                }
+            }
+        }
+        __syncthreads();
+    }
+}
 
-__global__ void __launch_bounds__(32) k_dec_units(DecodeParams p) {
-    __shared__ uint32_t ring[RING * 32];
-    const uint32_t lane = threadIdx.x;
-    const unsigned long long u = (unsigned long long)blockIdx.x * 32 + lane;
+// One channel of one frame: read_channel_data's ALPC arm (reader.rs:207-244) and decode_channel_int's case
+// split (decoder.rs:92-148) -> where the residual bits are, which predictor runs over them, where the samples go.
+__device__ __forceinline__ void lane_setup(const DecodeParams &p, unsigned long long u, unsigned long long n_units, uint32_t lane,
+                                           Lane &L, int32_t (&c12)[12], int32_t (&hist)[12], unsigned long long &rpos, uint32_t &rbytes) {
     const uint32_t C = p.channels;
-    const uint32_t keep = p.ctl[0] < p.n_toc ? p.ctl[0] : p.n_toc;
-    const unsigned long long n_units = (unsigned long long)keep * C;
     const uint8_t *f = p.file;
-
-    Lane L;
     L.n = 0; L.k = 0; L.src = M_ZERO; L.order = 0; L.shift = 0; L.fixed = false; L.ms = false; L.odd = (lane & 1u) != 0;
     L.pcm = f; L.pcm_bytes = 0; L.outp = p.out; L.stride = C;
-    int32_t c12[12], hist[12];
     #pragma unroll
     for (int j = 0; j < 12; j++) { c12[j] = 0; hist[j] = 0; }
-    unsigned long long rpos = 0; uint32_t rbytes = 0;
+    rpos = 0; rbytes = 0;
 
     if (u < n_units && p.ctl[1] == 0xFFFFFFFFu) {
         const uint32_t fi = (uint32_t)(u / C), ch = (uint32_t)(u % C);
@@ -419,24 +437,41 @@ __global__ void __launch_bounds__(32) k_dec_units(DecodeParams p) {
         }
         // Silence / reserved types: zeros (reader.rs:180, 246)
     }
-    L.rs = (uint32_t)__cvta_generic_to_shared(ring) + 4u * lane;
     L.msa = L.ms ? (L.odd ? 0xFFFFFFFFu : 1u) : 1u;
     L.msb = L.ms ? 1u : 0u;
     L.mshift = L.ms ? 1u : 0u;
-    L.any_pcm = __any_sync(FULL, L.src == M_PCM);
-    bits_init(L.rs, L.bits, f, p.len, L.src == M_RICE ? rpos : 0ull, L.src == M_RICE ? rbytes : 0u);
+}
 
+// One CTA = 32 units and two warps.  Rice decoding and the predictor are two serial chains per channel; run by one
+// warp they add up (and a lone warp has nobody to hide its stalls behind).  Warp 0 runs the bit reader, warp 1 the
+// predictor + mid/side + output, one block of BLK residuals apart, handing over through shared memory.
+__global__ void __launch_bounds__(64) k_dec_units(DecodeParams p) {
+    __shared__ uint32_t ring[RING * 32];
+    __shared__ uint32_t resbuf[2 * BLK * 32];
+    const uint32_t lane = threadIdx.x & 31u;
+    const bool reader = threadIdx.x < 32;
+    const unsigned long long u = (unsigned long long)blockIdx.x * 32 + lane;
+    const uint32_t keep = p.ctl[0] < p.n_toc ? p.ctl[0] : p.n_toc;
+    const unsigned long long n_units = (unsigned long long)keep * p.channels;
+
+    Lane L;
+    int32_t c12[12], hist[12];
+    unsigned long long rpos; uint32_t rbytes;
+    lane_setup(p, u, n_units, lane, L, c12, hist, rpos, rbytes);
+    const bool any_pcm = __any_sync(FULL, L.src == M_PCM);
     const uint32_t nmax = __reduce_max_sync(FULL, L.n);
     const int omax = (int)__reduce_max_sync(FULL, (uint32_t)L.order);
-    uint32_t i = 0;
-    const uint32_t warm = nmax < 12u ? nmax : 12u;
-    for (; i < warm; i++) synth_step(L, i, c12, hist);
-    if (!L.any_pcm) {                                      // raw PCM lanes (rare) take the generic step for the whole warp
-        if (omax <= 4) i = synth_blocks<4>(L, i, nmax, c12, hist);
-        else if (omax <= 8) i = synth_blocks<8>(L, i, nmax, c12, hist);
-        else i = synth_blocks<12>(L, i, nmax, c12, hist);
+    const uint32_t nblk = (nmax + BLK - 1) / BLK;
+    const uint32_t res0 = (uint32_t)__cvta_generic_to_shared(resbuf) + 4u * lane;
+    if (reader) {
+        L.rs = (uint32_t)__cvta_generic_to_shared(ring) + 4u * lane;
+        bits_init(L.rs, L.bits, p.file, p.len, L.src == M_RICE ? rpos : 0ull, L.src == M_RICE ? rbytes : 0u);
+        producer_loop(L, res0, nblk, any_pcm);
+    } else {
+        if (omax <= 4) consumer_loop<4>(L, res0, nblk, c12, hist);
+        else if (omax <= 8) consumer_loop<8>(L, res0, nblk, c12, hist);
+        else consumer_loop<12>(L, res0, nblk, c12, hist);
     }
-    for (; i < nmax; i++) synth_step(L, i, c12, hist);
 }
 
 }  // namespace
@@ -448,7 +483,7 @@ cudaError_t launch_decode_parse(const DecodeParams &p, cudaStream_t st) {
 }
 cudaError_t launch_decode_units(const DecodeParams &p, cudaStream_t st) {
     const unsigned long long units = (unsigned long long)p.n_toc * p.channels;
-    if (units) k_dec_units<<<(unsigned)((units + 31) / 32), 32, 0, st>>>(p);
+    if (units) k_dec_units<<<(unsigned)((units + 31) / 32), 64, 0, st>>>(p);
     return cudaGetLastError();
 }
 
