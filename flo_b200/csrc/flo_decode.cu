@@ -205,11 +205,12 @@ __device__ __forceinline__ uint32_t rice_slow(uint32_t rs, BitIn &b, uint32_t k)
     if (k) { r = (uint32_t)(b.buf >> (64 - k)); b.buf <<= k; b.nb -= (int)k; }
     return (q << k) | r;
 }
-// Common path, branch-free up to the fit test: append the word on hand when the window is half empty, count the
-// leading ones of the top word, cut the k remainder bits out with funnel shifts.
-__device__ __forceinline__ int32_t rice_next(uint32_t rs, BitIn &b, uint32_t k) {
+// Common path, free of branches: append the word on hand when the window is half empty (predicated), count the
+// leading ones of the top word, cut the k remainder bits out with funnel shifts.  Returns the zigzag code
+// (q << k | remainder).  When the code does not fit the bits on hand (ok false) nothing is consumed.
+__device__ __forceinline__ uint32_t rice_try(uint32_t rs, BitIn &b, uint32_t k, bool &ok) {
     uint32_t hi = (uint32_t)(b.buf >> 32), lo = (uint32_t)b.buf;
-    if (b.nb <= 32) {                                      // the low word of the window is empty (predicated, not a branch)
+    if (b.nb <= 32) {                                      // the low word of the window is empty
         const uint32_t w = be(b.nxt);
         hi |= __funnelshift_rc(w, 0u, (uint32_t)b.nb);
         lo = __funnelshift_lc(0u, w, 32u - (uint32_t)b.nb);
@@ -217,18 +218,45 @@ __device__ __forceinline__ int32_t rice_next(uint32_t rs, BitIn &b, uint32_t k) 
         b.rd++;
     }
     b.nxt = ring_at(rs, b.rd);                             // not needed before the next sample
-    const int run = __clz((int)~hi);                       // leading ones (32: the run leaves the top word)
-    const int used = run + 1 + (int)k;
-    b.buf = ((unsigned long long)hi << 32) | lo;
-    uint32_t u;
-    if (__builtin_expect(run < 32 && used <= b.nb, 1)) {
-        const uint32_t t = __funnelshift_lc(lo, hi, (uint32_t)(run + 1));
-        u = ((uint32_t)run << k) | __funnelshift_rc(t, 0u, 32u - k);
-        b.buf <<= used; b.nb -= used;                      // used <= 63
-    } else {
-        u = rice_slow(rs, b, k);
+    uint32_t run;                                          // leading ones of the top word; 0xFFFFFFFF when it is all ones
+    asm("bfind.shiftamt.u32 %0, %1;" : "=r"(run) : "r"(~hi));
+    const int used = (int)(run + 1u + k);
+    ok = run < 32u && used <= b.nb;
+    const uint32_t t = __funnelshift_lc(lo, hi, run + 1u);
+    const uint32_t u = (run << k) | __funnelshift_rc(t, 0u, 32u - k);
+    const unsigned long long w64 = ((unsigned long long)hi << 32) | lo;
+    b.buf = ok ? w64 << (used & 63) : w64;                 // used <= 63 when ok
+    b.nb -= ok ? used : 0;
+    return u;
+}
+__device__ __forceinline__ uint32_t rice_next_u(uint32_t rs, BitIn &b, uint32_t k) {
+    bool ok;
+    uint32_t u = rice_try(rs, b, k, ok);
+    if (__builtin_expect(!ok, 0)) u = rice_slow(rs, b, k);
+    return u;
+}
+__device__ __forceinline__ int32_t unzigzag(uint32_t u) { return (int32_t)(u >> 1) ^ -(int32_t)(u & 1u); }
+__device__ __forceinline__ uint32_t zigzag(int32_t r) { return ((uint32_t)r << 1) ^ (uint32_t)(r >> 31); }
+__device__ __forceinline__ int32_t rice_next(uint32_t rs, BitIn &b, uint32_t k) { return unzigzag(rice_next_u(rs, b, k)); }
+// Four codes as one transaction: the common path runs without a branch; if any of the four did not fit, the
+// reader state is rolled back and the four are redone one by one with the long-code path available.
+__device__ __forceinline__ void rice_quad(uint32_t rs, BitIn &b, uint32_t k, uint32_t (&u)[4]) {
+    const unsigned long long buf0 = b.buf;
+    const int nb0 = b.nb;
+    const uint32_t rd0 = b.rd, nxt0 = b.nxt;
+    bool ok0, ok1, ok2, ok3;
+    u[0] = rice_try(rs, b, k, ok0);
+    u[1] = rice_try(rs, b, k, ok1);
+    u[2] = rice_try(rs, b, k, ok2);
+    u[3] = rice_try(rs, b, k, ok3);
+    if (__builtin_expect(!(ok0 && ok1 && ok2 && ok3), 0)) {
+        b.buf = buf0; b.nb = nb0; b.rd = rd0; b.nxt = nxt0;
+        #pragma unroll 1
+        for (int j = 0; j < 4; j++) {
+            const uint32_t v = rice_next_u(rs, b, k);
+            if (j == 0) u[0] = v; else if (j == 1) u[1] = v; else if (j == 2) u[2] = v; else u[3] = v;
+        }
     }
-    return (int32_t)(u >> 1) ^ -(int32_t)(u & 1u);
 }
 
 __constant__ int c_fixed[5][4] = {{0, 0, 0, 0}, {1, 0, 0, 0}, {2, -1, 0, 0}, {3, -3, 1, 0}, {4, -6, 4, -1}};   // decoder.rs:199-259
@@ -291,7 +319,7 @@ template <int ORD>
 __device__ __forceinline__ void consume_block(const Lane &L, uint32_t res, uint32_t i0, const int32_t (&c)[ORD], int32_t (&h)[ORD], float *&op) {
     #pragma unroll
     for (int t = 0; t < BLK; t++) {
-        const int32_t s = fir<ORD>(c, h, L.shift, (int32_t)lds32(res + 128u * t));
+        const int32_t s = fir<ORD>(c, h, L.shift, unzigzag(lds32(res + 128u * t)));
         #pragma unroll
         for (int j = ORD - 1; j > 0; j--) h[j] = h[j - 1];
         h[0] = s;
@@ -329,7 +357,7 @@ __device__ __forceinline__ void consumer_loop(const Lane &L, uint32_t res0, uint
     for (uint32_t ph = 0; ph <= nblk; ph++) {
         if (ph == 1) {                                     // first block: warm-up rules, generic taps
             #pragma unroll 1
-            for (int t = 0; t < BLK; t++) synth_apply(L, (uint32_t)t, (int32_t)lds32(res0 + 128u * t), c12, hist);
+            for (int t = 0; t < BLK; t++) synth_apply(L, (uint32_t)t, unzigzag(lds32(res0 + 128u * t)), c12, hist);
             #pragma unroll
             for (int j = 0; j < ORD; j++) h[j] = hist[j];
         } else if (ph > 1) {
@@ -338,7 +366,7 @@ __device__ __forceinline__ void consumer_loop(const Lane &L, uint32_t res0, uint
         __syncthreads();
     }
 }
-// Bit-reading warp: residual i of every lane -> res[block parity][i % BLK][lane].
+// Bit-reading warp: residual i of every lane, as its zigzag code -> res[block parity][i % BLK][lane].
 __device__ __forceinline__ void producer_loop(Lane &L, uint32_t res0, uint32_t nblk, bool any_pcm) {
     for (uint32_t ph = 0; ph <= nblk; ph++) {
         if (ph < nblk) {
@@ -347,11 +375,16 @@ __device__ __forceinline__ void producer_loop(Lane &L, uint32_t res0, uint32_t n
             for (int g = 0; g < BLK; g += GROUP) {
                 topup(L.rs, L.bits);
                 if (!any_pcm) {
-                    #pragma unroll 2
-                    for (int t = 0; t < GROUP; t++) sts32(res + 128u * (g + t), (uint32_t)rice_next(L.rs, L.bits, L.k));
+                    #pragma unroll
+                    for (int t = 0; t < GROUP; t += 4) {
+                        uint32_t u[4];
+                        rice_quad(L.rs, L.bits, L.k, u);
+                        #pragma unroll
+                        for (int j = 0; j < 4; j++) sts32(res + 128u * (g + t + j), u[j]);
+                    }
                 } else {                                   // raw PCM lanes (rare): the generic source for the whole warp
                     #pragma unroll 1
-                    for (int t = 0; t < GROUP; t++) sts32(res + 128u * (g + t), (uint32_t)next_residual(L, ph * BLK + g + t));
+                    for (int t = 0; t < GROUP; t++) sts32(res + 128u * (g + t), zigzag(next_residual(L, ph * BLK + g + t)));
                 }
             }
         }
