@@ -98,11 +98,12 @@ __global__ void __launch_bounds__(1024) k_dec_scan(DecodeParams p) {
 // streams are staged through shared memory instead: a 32-word ring per lane (word-interleaved, bank = lane),
 // topped up at warp-uniform points with 16-byte loads that are stored to the ring one top-up later.  The
 // per-sample path is branch-free: one predicated 32-bit append and one unconditional LDS of the next word.
-constexpr int RING = 32;              // words per lane
-constexpr int GROUP = 8;              // samples between top-ups; the fast path pops at most one word per sample
+constexpr int RING = 64;              // words per lane
+constexpr int GROUP = 16;             // samples between top-ups (long enough for the loads of one top-up to land before the
+                                      // next stores them); the fast path pops at most one word per sample
 struct BitIn {
     const uint4 *gp, *vend;           // next vector to request; end of the readable image
-    uint4 p0, p1;                     // vectors in flight
+    uint4 p0, p1, p2, p3;             // vectors in flight
     uint32_t npend;
     uint32_t wr, rd;                  // ring word counters: next word to store / word held in nxt
     unsigned long long end_off;       // payload end, as a byte offset from the aligned base of the stream
@@ -136,13 +137,20 @@ __device__ __forceinline__ void put_vec(uint32_t rs, BitIn &b, const uint4 &v) {
     }
     b.wr += 4;
 }
-__device__ __forceinline__ void topup_once(uint32_t rs, BitIn &b) {
+__device__ __forceinline__ void store_pending(uint32_t rs, BitIn &b) {
     if (b.npend >= 1) put_vec(rs, b, b.p0);
-    if (b.npend == 2) put_vec(rs, b, b.p1);
+    if (b.npend >= 2) put_vec(rs, b, b.p1);
+    if (b.npend >= 3) put_vec(rs, b, b.p2);
+    if (b.npend >= 4) put_vec(rs, b, b.p3);
     b.npend = 0;
+}
+__device__ __forceinline__ void topup_once(uint32_t rs, BitIn &b) {
+    store_pending(rs, b);
     const uint32_t room = RING - (b.wr - b.rd);
     if (room >= 4) { b.p0 = ldv(b.gp, b.vend); b.gp++; b.npend = 1; }
     if (room >= 8) { b.p1 = ldv(b.gp, b.vend); b.gp++; b.npend = 2; }
+    if (room >= 12) { b.p2 = ldv(b.gp, b.vend); b.gp++; b.npend = 3; }
+    if (room >= 16) { b.p3 = ldv(b.gp, b.vend); b.gp++; b.npend = 4; }
 }
 // Warp-uniform.  Afterwards every lane holds at least 2 * GROUP words, so the fast path cannot run dry before the next call.
 __device__ __forceinline__ void topup(uint32_t rs, BitIn &b) {
@@ -157,7 +165,7 @@ __device__ __forceinline__ void bits_init(uint32_t rs, BitIn &b, const uint8_t *
     b.gp = nbytes ? (const uint4 *)a0 : b.vend;
     b.end_off = (unsigned long long)sk + nbytes;
     b.npend = 0; b.wr = 0; b.rd = 0;
-    b.p0 = b.p1 = make_uint4(0u, 0u, 0u, 0u);
+    b.p0 = b.p1 = b.p2 = b.p3 = make_uint4(0u, 0u, 0u, 0u);
     topup(rs, b);
     b.rd = sk >> 2;                                        // the payload starts sk bytes into the first vector
     const uint32_t sb = sk & 3u;
@@ -170,7 +178,7 @@ __device__ __forceinline__ void bits_init(uint32_t rs, BitIn &b, const uint8_t *
 // lane-private (divergent) fill: at least `want` words on hand; fetches synchronously when the ring is dry
 __device__ __forceinline__ void lane_fill(uint32_t rs, BitIn &b, int want) {
     while ((int)(b.wr - b.rd) < want) {
-        if (b.npend) { put_vec(rs, b, b.p0); if (b.npend == 2) put_vec(rs, b, b.p1); b.npend = 0; }
+        if (b.npend) store_pending(rs, b);
         else { b.p0 = ldv(b.gp, b.vend); b.gp++; b.npend = 1; }
     }
 }
@@ -300,7 +308,7 @@ __device__ __forceinline__ void emit(const Lane &L, uint32_t i, int32_t s) {
 }
 
 // ---- predictor side ----
-constexpr int BLK = 16;               // samples handed from the bit-reading warp to the predictor warp at a time
+constexpr int BLK = GROUP;            // samples handed from the bit-reading warp to the predictor warp at a time
 
 template <int ORD>
 __device__ __forceinline__ int32_t fir(const int32_t (&c)[ORD], const int32_t (&h)[ORD], int sh, int32_t r) {
