@@ -308,7 +308,7 @@ def main() -> int:
                             "launches": ts[-1]["launches"], "round_trip_exact": bool(n_dec == total_inter and torch.equal(d_dec, q)),
                             "pct_of_hbm_peak": 100.0 * (4.0 * total_inter + float(l2[0])) / (k_dec * 1e-3) / 1e9 / peak,
                             "note": "flo_decode_device on the level-5 file of the same stream; latency-bound (one lane per "
-                                    "channel of a frame), see DESIGN.md section 9.2"}
+                                    "channel of a frame, reader warp + predictor warp), see DESIGN.md section 9.2"}
         del d_dec, q
 
     # e2e: host buffers through the reference-facing C-ABI call (H2D + D2H inside the timed region)
