@@ -9,7 +9,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 # FLO_B200_SO selects an experimental build of the same library (see build.py); never a different implementation
 SO_PATH = os.environ.get("FLO_B200_SO") or os.path.join(_HERE, "libflo_b200.so")
 
-FMT_F32, FMT_PCM16 = 0, 1
+FMT_F32, FMT_PCM16, FMT_U8, FMT_S32 = 0, 1, 2, 3
 
 
 class FloError(RuntimeError):

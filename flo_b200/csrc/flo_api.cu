@@ -167,6 +167,7 @@ struct flo_ctx {
     cudaEvent_t ev_in[MAX_WAVES] = {}, ev_k[MAX_WAVES] = {}, ev_fin = nullptr;
     DevBuf in, out, meta, tracks, frames, ctrl, fexcl, fsize, foff, plane, cres, report;
     DevBuf dec_frames, dec_units, dec_base, dec_ctl;      // decoder scratch
+    DevBuf conv;                                           // f32 samples of the U8 / S32 ingest pre-pass
     uint64_t counters[24] = {0};      // [0..7] analysis counters, [8..23] per-phase SM clock sums
     HostBuf h_small, h_out;
     bool report_on = false;
@@ -226,7 +227,7 @@ extern "C" void flo_ctx_destroy(flo_ctx *c) {
     cudaDeviceSynchronize();
     if (c->l2_win_ptr) { cudaCtxResetPersistingL2Cache(); cudaGetLastError(); }
     for (DevBuf *b : {&c->in, &c->out, &c->meta, &c->tracks, &c->frames, &c->ctrl, &c->fexcl, &c->fsize,
-                      &c->foff, &c->plane, &c->cres, &c->report, &c->dec_frames, &c->dec_units, &c->dec_base, &c->dec_ctl})
+                      &c->foff, &c->plane, &c->cres, &c->report, &c->dec_frames, &c->dec_units, &c->dec_base, &c->dec_ctl, &c->conv})
         b->release();
     c->h_small.release();
     c->h_out.release();
@@ -296,8 +297,10 @@ struct Layout {
 // worst-case bytes of one frame: 6 + C * (4 + 1 + 48 + 3 + 2 n)   (types.rs:242-267, raw payload bound)
 inline uint64_t frame_bound(uint64_t cl0, uint64_t C) { return 6 + C * (4 + 52 + 2 * cl0); }
 
+inline size_t fmt_size(int format) { return format == FLO_FMT_PCM16 ? 2 : format == FLO_FMT_U8 ? 1 : 4; }
+
 int make_layout(const flo_track *tracks, size_t n_tracks, int format, Layout &L) {
-    const size_t esz = format == FLO_FMT_PCM16 ? 2 : 4;
+    const size_t esz = fmt_size(format);
     L.tr.resize(n_tracks);
     L.in_off.resize(n_tracks);
     uint64_t stat = 0, frames = 0, segs = 0, bound = 0, meta = 0, inb = 0;
@@ -362,15 +365,22 @@ extern "C" size_t flo_output_bound(const flo_track *tracks, size_t n_tracks) {
 static int encode_batch_impl(flo_ctx *c, const flo_track *tracks, size_t n_tracks, int format, uint8_t level,
                              bool host_inputs, void *d_out, size_t d_out_cap, uint64_t *offsets, uint64_t *lens,
                              OutBlock **sink = nullptr) {
-    if (format != FLO_FMT_F32 && format != FLO_FMT_PCM16) { set_err("unknown sample format %d", format); return FLO_ERR_ARG; }
+    if (format != FLO_FMT_F32 && format != FLO_FMT_PCM16 && format != FLO_FMT_U8 && format != FLO_FMT_S32) { set_err("unknown sample format %d", format); return FLO_ERR_ARG; }
+    const bool convert = format == FLO_FMT_U8 || format == FLO_FMT_S32;     // pre-pass to f32, then the f32 path
     if (n_tracks == 0) return FLO_OK;
     if (level > 9) level = 9;                                          // with_compression, encoder.rs:26-29
     CK(cudaSetDevice(c->device));
     Layout L;
     int rc = make_layout(tracks, n_tracks, format, L);
     if (rc) return rc;
-    const size_t esz = format == FLO_FMT_PCM16 ? 2 : 4;
+    const size_t esz = fmt_size(format);
     cudaStream_t st = c->stream;
+    std::vector<uint64_t> conv_off(convert ? n_tracks : 0);
+    if (convert) {
+        uint64_t cb = 0;
+        for (size_t t = 0; t < n_tracks; t++) { conv_off[t] = cb; cb += align_up(tracks[t].n_interleaved * 4, 256); }
+        if ((rc = c->conv.reserve(std::max<uint64_t>(cb, 1)))) return rc;
+    }
 
     uint8_t *out = (uint8_t *)d_out;
     if (!out) {
@@ -447,7 +457,7 @@ static int encode_batch_impl(flo_ctx *c, const flo_track *tracks, size_t n_track
     // H2D copy of wave w+1 overlaps the encode kernel of wave w (frames are independent; the look-back
     // status words carry the running byte offset from one launch to the next).
     int n_waves = 1;
-    if (host_inputs && NF >= 2u * (uint32_t)grid * 2u) n_waves = (int)std::min<uint32_t>(MAX_WAVES, NF / (3u * (uint32_t)grid));
+    if (host_inputs && !convert && NF >= 2u * (uint32_t)grid * 2u) n_waves = (int)std::min<uint32_t>(MAX_WAVES, NF / (3u * (uint32_t)grid));
     if (n_waves < 1) n_waves = 1;
     std::vector<uint32_t> wave_end(n_waves);
     for (int w = 0; w < n_waves; w++) wave_end[w] = (uint32_t)((uint64_t)NF * (w + 1) / n_waves);
@@ -465,6 +475,9 @@ static int encode_batch_impl(flo_ctx *c, const flo_track *tracks, size_t n_track
             if (((uintptr_t)tracks[t].samples & (esz - 1)) != 0) { set_err("track %zu: device samples pointer not aligned to the sample size", t); return FLO_ERR_ARG; }
         }
     }
+    std::vector<const void *> raw_src(convert ? n_tracks : 0);
+    if (convert)
+        for (size_t t = 0; t < n_tracks; t++) { raw_src[t] = L.tr[t].samples; L.tr[t].samples = (const uint8_t *)c->conv.p + conv_off[t]; }
     uint8_t *hs = (uint8_t *)c->h_small.p;
     memcpy(hs, L.tr.data(), sizeof(TrackDev) * n_tracks);
     uint8_t *hmeta = hs + sizeof(TrackDev) * n_tracks;
@@ -480,7 +493,7 @@ static int encode_batch_impl(flo_ctx *c, const flo_track *tracks, size_t n_track
     ep.tracks = (const TrackDev *)c->tracks.p;
     ep.frames = (const uint2 *)c->frames.p;
     ep.n_frames = NF;
-    ep.format = format;
+    ep.format = convert ? FLO_FMT_F32 : format;
     ep.level = level;
     ep.out = out;
     ep.status = (unsigned long long *)c->ctrl.p;
@@ -555,6 +568,13 @@ static int encode_batch_impl(flo_ctx *c, const flo_track *tracks, size_t n_track
                 cudaError_t e = cudaEventRecord(c->ev_in[w], s_in);
                 if (e == cudaSuccess) e = cudaStreamWaitEvent(st, c->ev_in[w], 0);
                 if (e != cudaSuccess) return fail(e, "stream ordering failed");
+            }
+        }
+        if (convert) {                                     // single wave: the whole batch is resident here
+            for (size_t t = 0; t < n_tracks; t++) {
+                cudaError_t e = launch_ingest_convert(raw_src[t], (float *)((uint8_t *)c->conv.p + conv_off[t]), tracks[t].n_interleaved, format, st);
+                if (e != cudaSuccess) return fail(e, "ingest pre-pass failed");
+                launches += tracks[t].n_interleaved ? 1 : 0;
             }
         }
         ep.frame_begin = g0; ep.frame_end = g1; ep.ticket = n_waves > 1 ? wave_ticket + w : ctl;

@@ -103,6 +103,8 @@ cudaError_t launch_toc(const FinalParams &p, cudaStream_t st);
 cudaError_t launch_crc_segments(const FinalParams &p, cudaStream_t st);
 cudaError_t launch_headers(const FinalParams &p, cudaStream_t st);
 void upload_crc_tables();
+// reflo's U8 / S32 ingest arms (reflo/src/audio.rs:255-269) as a pre-pass: interleaved PCM -> interleaved f32
+cudaError_t launch_ingest_convert(const void *src, float *dst, unsigned long long n, int format, cudaStream_t st);
 
 // ---- lossless decoder (libflo/src/reader.rs + libflo/src/lossless/decoder.rs) ----
 enum DecErr : uint32_t { DEC_TOO_MANY = 1, DEC_BAD_ORDER = 2, DEC_EOF = 3, DEC_TRANSFORM = 4, DEC_BAD_K = 5 };

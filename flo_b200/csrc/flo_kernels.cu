@@ -261,4 +261,25 @@ cudaError_t launch_headers(const FinalParams &p, cudaStream_t st) {
 }
 
 
+
+// reflo's remaining ingest arms (append_samples, reflo/src/audio.rs:255-269), element-wise and exact in f32:
+//   S32: s as f32 * (1.0 / 2147483648.0)        U8: (s as f32 - 128.0) / 128.0
+// A separate pre-pass (one extra read + write of the samples) so that the encode kernel keeps its two ingest forms.
+__global__ void k_ingest_convert(const void *src, float *dst, unsigned long long n, int format) {
+    const unsigned long long stride = (unsigned long long)gridDim.x * blockDim.x;
+    for (unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+        float v;
+        if (format == FLO_FMT_S32) v = __fmul_rn(__int2float_rn(reinterpret_cast<const int32_t *>(src)[i]), 1.0f / 2147483648.0f);
+        else v = __fdiv_rn(__fsub_rn((float)reinterpret_cast<const uint8_t *>(src)[i], 128.0f), 128.0f);
+        dst[i] = v;
+    }
+}
+cudaError_t launch_ingest_convert(const void *src, float *dst, unsigned long long n, int format, cudaStream_t st) {
+    if (n == 0) return cudaSuccess;
+    const unsigned long long want = (n + 255) / 256;
+    const unsigned grid = (unsigned)(want < 148ull * 16 ? want : 148ull * 16);
+    k_ingest_convert<<<grid, 256, 0, st>>>(src, dst, n, format);
+    return cudaGetLastError();
+}
+
 }  // namespace flo

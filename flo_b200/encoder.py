@@ -17,7 +17,7 @@ from typing import List, Optional, Sequence, Tuple
 import numpy as np
 
 from . import _lib
-from ._lib import FMT_F32, FMT_PCM16, FloError
+from ._lib import FMT_F32, FMT_PCM16, FMT_S32, FMT_U8, FloError
 
 
 class Context:
@@ -81,7 +81,7 @@ class Context:
             return []
         arr = (_lib.Track * n)()
         keep = []
-        dt = np.float32 if fmt == FMT_F32 else np.int16
+        dt = {FMT_F32: np.float32, FMT_PCM16: np.int16, FMT_U8: np.uint8, FMT_S32: np.int32}[fmt]
         for i, t in enumerate(tracks):
             s = np.ascontiguousarray(t.samples, dtype=dt).reshape(-1)
             m = bytes(t.metadata or b"")
@@ -265,6 +265,16 @@ class Encoder:
         """Encoder::encode(&self, samples: &[f32], metadata: &[u8]) -> FloResult<Vec<u8>> (encoder.rs:32-45)."""
         t = TrackSpec(np.asarray(samples, dtype=np.float32), self.sample_rate, self.channels, self.bit_depth, metadata)
         return self._context().encode_batch([t], self.compression_level, FMT_F32)[0]
+
+    def encode_pcm(self, pcm, metadata: bytes = b"") -> bytes:
+        """reflo's integer ingest arms (reflo/src/audio.rs:247-269) + Encoder::encode, on the device: the array's
+        dtype picks the arm (uint8, int16 or int32)."""
+        a = np.asarray(pcm)
+        fmt = {np.dtype(np.uint8): FMT_U8, np.dtype(np.int16): FMT_PCM16, np.dtype(np.int32): FMT_S32}.get(a.dtype)
+        if fmt is None:
+            raise FloError(f"unsupported PCM dtype {a.dtype}")
+        t = TrackSpec(a, self.sample_rate, self.channels, self.bit_depth, metadata)
+        return self._context().encode_batch([t], self.compression_level, fmt)[0]
 
     def encode_pcm16(self, pcm, metadata: bytes = b"") -> bytes:
         """reflo's S16 ingest (reflo/src/audio.rs:247-254) + Encoder::encode, fused on the device."""

@@ -104,3 +104,44 @@ def encode_from_samples(samples, sample_rate: int, channels: int, level: int = 5
     x = np.ascontiguousarray(samples, dtype=np.float32).reshape(-1)
     meta = reflo_metadata(x.size, sample_rate, channels, level, encoding_time, source_format, original_filename, tags)
     return Encoder(sample_rate, channels, 16, context=context).with_compression(level).encode(x, meta)
+
+
+# ---- WAV front (first half): RIFF parsing on the host, sample conversion on the device --------
+def parse_wav(data: bytes):
+    """Minimal RIFF/WAVE reader -> (interleaved numpy array, sample_rate, channels).  The array keeps the file's
+    sample type (uint8 / int16 / int32 / float32), which selects reflo's ingest arm (reflo/src/audio.rs:238-270).
+    24-bit PCM and compressed formats are refused."""
+    if len(data) < 12 or data[:4] != b"RIFF" or data[8:12] != b"WAVE":
+        raise FloError("not a RIFF/WAVE file")
+    pos, fmt, body = 12, None, None
+    while pos + 8 <= len(data):
+        cid, size = data[pos:pos + 4], struct.unpack_from("<I", data, pos + 4)[0]
+        chunk = data[pos + 8:pos + 8 + size]
+        if cid == b"fmt ":
+            fmt = chunk
+        elif cid == b"data":
+            body = chunk
+            break
+        pos += 8 + size + (size & 1)
+    if fmt is None or body is None or len(fmt) < 16:
+        raise FloError("WAVE file without fmt/data chunk")
+    tag, channels, sample_rate, _, _, bits = struct.unpack_from("<HHIIHH", fmt, 0)
+    if tag == 0xFFFE and len(fmt) >= 26:                                      # WAVE_FORMAT_EXTENSIBLE: sub-format GUID
+        tag = struct.unpack_from("<H", fmt, 24)[0]
+    dt = {(1, 8): np.uint8, (1, 16): np.dtype("<i2"), (1, 32): np.dtype("<i4"), (3, 32): np.dtype("<f4")}.get((tag, bits))
+    if dt is None or channels == 0:
+        raise FloError(f"unsupported WAVE format (tag {tag}, {bits} bits, {channels} channels)")
+    isz = np.dtype(dt).itemsize
+    n = len(body) // (isz * channels) * channels
+    return np.frombuffer(body, dtype=dt, count=n), int(sample_rate), int(channels)
+
+
+def encode_wav(wav: bytes, level: int = 5, *, encoding_time: str, source_format: Optional[str] = "WAV",
+               original_filename: Optional[str] = None, tags: Optional[Dict[str, Union[str, int]]] = None,
+               context: Optional[Context] = None) -> bytes:
+    """`reflo encode in.wav` for PCM WAV input (reflo/src/lib.rs:202-309 after reflo/src/audio.rs:238-270): the
+    samples go to the device in the file's own integer type and are converted there."""
+    x, sr, ch = parse_wav(wav)
+    meta = reflo_metadata(x.size, sr, ch, level, encoding_time, source_format, original_filename, tags)
+    enc = Encoder(sr, ch, 16, context=context).with_compression(level)
+    return enc.encode(x, meta) if x.dtype == np.float32 else enc.encode_pcm(x, meta)

@@ -40,6 +40,8 @@ extern "C" {
 /* sample formats of the batched entries */
 #define FLO_FMT_F32    0      /* interleaved f32, the documented Encoder::encode input (encoder.rs:32) */
 #define FLO_FMT_PCM16  1      /* interleaved i16 PCM: reflo's S16 ingest arm, s * (1/32768) (reflo/src/audio.rs:247-254), then as F32 */
+#define FLO_FMT_U8     2      /* interleaved u8 PCM: reflo's U8 arm, (s - 128) / 128 (reflo/src/audio.rs:263-269), then as F32 */
+#define FLO_FMT_S32    3      /* interleaved i32 PCM: reflo's S32 arm, s as f32 * (1/2147483648) (reflo/src/audio.rs:255-262), then as F32 */
 
 typedef struct flo_ctx flo_ctx;
 

@@ -438,3 +438,14 @@ class StreamingEncoderRef:
         out += toc + data + bytes(metadata)
         self.pending = []
         return out
+
+
+# ---- reflo's other ingest arms (reflo/src/audio.rs:255-269), numpy f32 arithmetic --------------------------
+def s32_to_f32(pcm) -> np.ndarray:
+    """S32 arm: `s as f32 * (1.0 / 2147483648.0)` (audio.rs:255-262)."""
+    return np.asarray(pcm, np.int32).astype(np.float32) * np.float32(1.0 / 2147483648.0)
+
+
+def u8_to_f32(pcm) -> np.ndarray:
+    """U8 arm: `(s as f32 - 128.0) / 128.0` (audio.rs:263-269)."""
+    return (np.asarray(pcm, np.uint8).astype(np.float32) - np.float32(128.0)) / np.float32(128.0)

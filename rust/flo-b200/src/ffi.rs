@@ -49,6 +49,8 @@ pub struct flo_info {
 
 pub const FLO_FMT_F32: c_int = 0;
 pub const FLO_FMT_PCM16: c_int = 1;
+pub const FLO_FMT_U8: c_int = 2;
+pub const FLO_FMT_S32: c_int = 3;
 
 extern "C" {
     pub fn flo_ctx_create(device: c_int, out: *mut *mut flo_ctx) -> c_int;

@@ -410,3 +410,39 @@ def test_seeded_random_sweep(fb, ctx):
     got = ctx.encode_batch(specs, 5, fb.FMT_PCM16)
     for i, (g, w) in enumerate(zip(got, want)):
         check_same(g, w, f"batched level-5 case {i}")
+
+
+# ---- reflo's U8 / S32 ingest arms (row N4, first half) ------------------------------------------------------------
+@pytest.mark.gpu
+@pytest.mark.parametrize("channels,level,n", [(1, 5, 20000), (2, 5, 36001), (2, 9, 8000), (6, 3, 12345)])
+def test_s32_and_u8_entries_match_oracle(channels, level, n):
+    import flo_b200
+    sr = 16000
+    rng = np.random.default_rng(n + channels)
+    base = synth_pcm16(n, channels, sr, seed=n, kind="speech").astype(np.int64)
+    s32 = (base * 65536 + rng.integers(-40000, 40000, base.size)).clip(-2**31, 2**31 - 1).astype(np.int32)
+    s32[:7] = [-2**31, 2**31 - 1, 0, 1, -1, 65535, -65536][: min(7, s32.size)]
+    u8 = ((base >> 8) + 128).clip(0, 255).astype(np.uint8)
+    u8[:4] = [0, 255, 128, 127]
+    enc = flo_b200.Encoder(sr, channels, 16).with_compression(level)
+    assert enc.encode_pcm(s32, b"m") == oracle.encode(oracle.s32_to_f32(s32), sr, channels, 16, level, b"m")
+    assert enc.encode_pcm(u8, b"") == oracle.encode(oracle.u8_to_f32(u8), sr, channels, 16, level, b"")
+    assert enc.encode_pcm(u8) == enc.encode(oracle.u8_to_f32(u8))            # same bytes as the f32 entry
+
+
+@pytest.mark.gpu
+def test_s32_device_entry_and_batch():
+    import flo_b200
+    import torch
+    sr, ch = 44100, 2
+    pcm = synth_pcm16(sr * 3 + 17, ch, sr, seed=5).astype(np.int32) * 65536 + 12345
+    ctx = flo_b200.default_context()
+    d_in = torch.from_numpy(pcm).cuda()
+    bound = ctx.output_bound([pcm.size, pcm.size // 2], [sr, sr], [ch, ch])
+    d_out = torch.empty(bound, dtype=torch.uint8, device="cuda")
+    offs, lens = ctx.encode_batch_device([d_in.data_ptr(), d_in.data_ptr()], [pcm.size, pcm.size // 2], [sr, sr], [ch, ch], [16, 16],
+                                         d_out.data_ptr(), bound, level=5, fmt=flo_b200.FMT_S32)
+    host = d_out.cpu().numpy()
+    for i, n in enumerate([pcm.size, pcm.size // 2]):
+        got = host[int(offs[i]):int(offs[i]) + int(lens[i])].tobytes()
+        assert got == oracle.encode(oracle.s32_to_f32(pcm[:n]), sr, ch, 16, 5, b"")

@@ -82,3 +82,46 @@ def test_config1_audio_wav_all_246_bytes():
     gold = golden_bytes("audio_lossless.flo")
     out = reflo.encode_from_samples(x, sr, ch, 5, encoding_time="2026-03-09T20:46:05Z", source_format="UNKNOWN")
     assert len(out) == 246 and out == gold
+
+
+def _wav(samples: np.ndarray, sr: int, ch: int, tag: int) -> bytes:
+    import struct
+    bits = samples.dtype.itemsize * 8
+    fmt = struct.pack("<HHIIHH", tag, ch, sr, sr * ch * bits // 8, ch * bits // 8, bits)
+    body = samples.tobytes()
+    return b"RIFF" + struct.pack("<I", 36 + len(body)) + b"WAVE" + b"fmt " + struct.pack("<I", 16) + fmt + \
+        b"LIST" + struct.pack("<I", 4) + b"INFO" + b"data" + struct.pack("<I", len(body)) + body
+
+
+def test_parse_wav_types():
+    for arr, tag in [(np.arange(200, dtype=np.uint8), 1), (np.arange(-100, 100, dtype=np.int16), 1),
+                     (np.arange(-100, 100, dtype=np.int32) * 70000, 1), (np.linspace(-1, 1, 200).astype(np.float32), 3)]:
+        x, sr, ch = reflo.parse_wav(_wav(arr, 22050, 2, tag))
+        assert (sr, ch) == (22050, 2) and x.dtype == arr.dtype and np.array_equal(x, arr)
+    with pytest.raises(Exception):
+        reflo.parse_wav(b"RIFF0000WAVE")
+    with pytest.raises(Exception):
+        reflo.parse_wav(_wav(np.zeros(30, np.uint8), 8000, 1, 85))          # compressed format tag
+
+
+@pytest.mark.gpu
+def test_encode_wav_reproduces_the_shipped_file():
+    """`reflo encode audio.wav` -> Examples/audio_lossless.flo, all 246 bytes, from the WAV bytes themselves."""
+    import gzip
+    import os
+    from helpers import GOLDEN
+    wav = gzip.open(os.path.join(GOLDEN, "audio.wav.gz"), "rb").read()
+    out = reflo.encode_wav(wav, 5, encoding_time="2026-03-09T20:46:05Z", source_format="UNKNOWN")
+    assert out == golden_bytes("audio_lossless.flo")
+
+
+@pytest.mark.gpu
+def test_encode_wav_integer_arms():
+    sr = 8000
+    rng = np.random.default_rng(7)
+    for arr in [rng.integers(0, 256, sr * 2 + 5, dtype=np.int64).astype(np.uint8),
+                (rng.integers(-2**31, 2**31, sr * 2 + 4, dtype=np.int64)).astype(np.int32) >> 4]:
+        x = oracle.u8_to_f32(arr) if arr.dtype == np.uint8 else oracle.s32_to_f32(arr)
+        meta = reflo.reflo_metadata(arr.size // 2 * 2, sr, 2, 5, "2026-01-01T00:00:00Z", "WAV")
+        assert reflo.encode_wav(_wav(arr, sr, 2, 1), 5, encoding_time="2026-01-01T00:00:00Z") == \
+            oracle.encode(x[: arr.size // 2 * 2], sr, 2, 16, 5, meta)
