@@ -865,6 +865,10 @@ int decode_impl(flo_ctx *c, const uint8_t *h_file, const void *d_file, size_t le
 
     OutBlock *blk = nullptr;
     float *h_out = nullptr;
+    struct Guard {                                         // releases the result buffer on every early return
+        OutBlock *&blk; float *&h_out; cudaStream_t st; bool armed = true;
+        ~Guard() { if (!armed) return; cudaStreamSynchronize(st); cudaGetLastError(); if (blk) drop_block(blk); else free(h_out); }
+    } guard{blk, h_out, st};
     if (h_file) {
         const size_t bytes = (size_t)n * sizeof(float);
         if (bytes >= SMALL_OUTPUT) {
@@ -875,10 +879,7 @@ int decode_impl(flo_ctx *c, const uint8_t *h_file, const void *d_file, size_t le
             h_out = (float *)malloc(bytes ? bytes : 1);
             if (!h_out) { set_err("malloc(%zu) failed", bytes); return FLO_ERR_NOMEM; }
         }
-        if (bytes) {
-            cudaError_t e = cudaMemcpyAsync(h_out, d_out, bytes, cudaMemcpyDeviceToHost, st);
-            if (e != cudaSuccess) { if (blk) drop_block(blk); else free(h_out); CK(e); }
-        }
+        if (bytes) CK(cudaMemcpyAsync(h_out, d_out, bytes, cudaMemcpyDeviceToHost, st));
     }
     cudaEventRecord(c->ev[5], st);
     cudaError_t e = cudaStreamSynchronize(st);
@@ -887,10 +888,10 @@ int decode_impl(flo_ctx *c, const uint8_t *h_file, const void *d_file, size_t le
     else if (hc[9] != 0xFFFFFFFFu && (hc[9] >> 13) < keep) rc = decode_error(hc[9]);
     else if (H.tail_eof) { set_err("Unexpected end of file"); rc = FLO_ERR_ARG; }
     if (rc) {
-        if (blk) drop_block(blk); else free(h_out);
         *n_out = 0;
         return rc;
     }
+    guard.armed = false;
     if (h_file) {
         if (blk) publish_block(blk, 1);
         *out = h_out;

@@ -233,8 +233,9 @@ __device__ __forceinline__ uint32_t rice_try(uint32_t rs, BitIn &b, uint32_t k, 
     const uint32_t t = __funnelshift_lc(lo, hi, run + 1u);
     const uint32_t u = (run << k) | __funnelshift_rc(t, 0u, 32u - k);
     const unsigned long long w64 = ((unsigned long long)hi << 32) | lo;
-    b.buf = ok ? w64 << (used & 63) : w64;                 // used <= 63 when ok
-    b.nb -= ok ? used : 0;
+    const int take = ok ? used : 0;                        // used <= 63 when ok
+    b.buf = w64 << take;
+    b.nb -= take;
     return u;
 }
 __device__ __forceinline__ uint32_t rice_next_u(uint32_t rs, BitIn &b, uint32_t k) {
