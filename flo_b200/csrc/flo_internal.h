@@ -20,7 +20,10 @@ constexpr int MAXORD = 12;
 constexpr int NCAND = 14;             // raw, fixed 0..4, lpc 5..12
 constexpr int REPORT_CH = 8;          // channels per frame covered by the parity report
 constexpr uint32_t FILE_HDR = 70;     // magic(4) + header(66), writer.rs:132-191
-constexpr uint32_t CRC_SEG = 65536;   // bytes of DATA per CRC segment
+#ifndef FLO_CRC_SEG
+#define FLO_CRC_SEG 65536
+#endif
+constexpr uint32_t CRC_SEG = FLO_CRC_SEG;   // bytes of DATA per CRC segment
 constexpr int CRC_NT = 256;
 
 // One track of the batch (device copy).
