@@ -275,3 +275,33 @@ def test_device_resident_round_trip(fb):
     assert torch.equal(d_out, q * torch.tensor(1.0 / 32767.0, dtype=torch.float32, device="cuda"))
     with pytest.raises(fb.FloError):
         ctx.decode_device(d_file.data_ptr() + int(offs[0]), int(lens[0]), d_out.data_ptr(), 10)
+
+
+def test_decode_on_caller_stream_and_concurrent_contexts(fb):
+    """Two contexts decoding from two threads, one of them on a caller-owned stream; results stay bit-exact."""
+    import threading
+    import torch
+    sr = 22050
+    files = [fb.Encoder(sr, 2, 16).with_compression(lv).encode_pcm16(synth_pcm16(sr * 6 + 11 * lv, 2, sr, seed=40 + lv)) for lv in (3, 5, 8)]
+    wants = [oracle.decode(f) for f in files]
+    ctxs = [fb.Context(0), fb.Context(0)]
+    stream = torch.cuda.Stream()
+    ctxs[1].set_stream(stream.cuda_stream)
+    errs = []
+
+    def work(ci):
+        try:
+            for rep in range(6):
+                for f, w in zip(files, wants):
+                    got, info = ctxs[ci].decode(f)
+                    assert same_f32(np.asarray(got), w) and info["channels"] == 2
+        except Exception as e:          # surfaced in the main thread
+            errs.append(e)
+
+    ts = [threading.Thread(target=work, args=(i,)) for i in range(2)]
+    [t.start() for t in ts]
+    [t.join() for t in ts]
+    ctxs[1].set_stream(0)
+    for c in ctxs:
+        c.close()
+    assert not errs, errs
