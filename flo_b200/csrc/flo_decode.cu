@@ -384,12 +384,23 @@ __device__ __forceinline__ void producer_loop(Lane &L, uint32_t res0, uint32_t n
             for (int g = 0; g < BLK; g += GROUP) {
                 topup(L.rs, L.bits);
                 if (!any_pcm) {
+                    // The whole group as one transaction: GROUP codes straight-line with predication only; if any of
+                    // them did not fit the bits on hand, roll the reader back and redo the group code by code.
+                    BitIn &b = L.bits;
+                    const unsigned long long buf0 = b.buf;
+                    const int nb0 = b.nb;
+                    const uint32_t rd0 = b.rd, nxt0 = b.nxt;
+                    uint32_t u[GROUP];
+                    bool all_ok = true;
                     #pragma unroll
-                    for (int t = 0; t < GROUP; t += 4) {
-                        uint32_t u[4];
-                        rice_quad(L.rs, L.bits, L.k, u);
+                    for (int t = 0; t < GROUP; t++) { bool ok; u[t] = rice_try(L.rs, b, L.k, ok); all_ok = all_ok && ok; }
+                    if (__builtin_expect(!all_ok, 0)) {
+                        b.buf = buf0; b.nb = nb0; b.rd = rd0; b.nxt = nxt0;
+                        #pragma unroll 1
+                        for (int t = 0; t < GROUP; t++) sts32(res + 128u * (g + t), rice_next_u(L.rs, b, L.k));
+                    } else {
                         #pragma unroll
-                        for (int j = 0; j < 4; j++) sts32(res + 128u * (g + t + j), u[j]);
+                        for (int t = 0; t < GROUP; t++) sts32(res + 128u * (g + t), u[t]);
                     }
                 } else {                                   // raw PCM lanes (rare): the generic source for the whole warp
                     #pragma unroll 1
