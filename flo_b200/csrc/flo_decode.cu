@@ -424,7 +424,10 @@ __device__ __forceinline__ void lane_setup(const DecodeParams &p, unsigned long 
     for (int j = 0; j < 12; j++) { c12[j] = 0; hist[j] = 0; }
     rpos = 0; rbytes = 0;
 
-    if (u < n_units && p.ctl[1] == 0xFFFFFFFFu) {
+    // an error in a frame the reader never reaches (behind its stop entry) does not count (reader.rs:116-118)
+    const uint32_t errkey = p.ctl[1];
+    const bool failed = errkey != 0xFFFFFFFFu && (errkey >> 13) < (p.ctl[0] < p.n_toc ? p.ctl[0] : p.n_toc);
+    if (u < n_units && !failed) {
         const uint32_t fi = (uint32_t)(u / C), ch = (uint32_t)(u % C);
         const DecFrame fr = p.frames[fi];
         const DecUnit un = p.units[u];

@@ -207,6 +207,9 @@ def test_toc_break_and_overlapping_offsets(fb):
     want = check(fb, data)
     assert want.size == 3 * n
     assert check(fb, build_file(1, frames, data_size=10 + len(ch) + 3)).size == 2 * n     # frame starting before data_end is read
+    bad = (3, n, 0, [bytes([13]) + ch[1:]])                                               # invalid LPC order ...
+    flen = 10 + len(ch)
+    assert check(fb, build_file(1, [frames[0], frames[0], bad], toc_offsets=[0, 10 ** 9, 2 * flen])).size == n   # ... behind the stop entry: never read
 
 
 def test_empty_and_degenerate_files(fb):
