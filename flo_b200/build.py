@@ -14,7 +14,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 SO = os.path.join(HERE, "libflo_b200.so")
 SOURCES = ["flo_encode_nt512.cu", "flo_encode_nt256.cu", "flo_encode_nt128.cu", "flo_kernels.cu", "flo_decode.cu", "flo_api.cu"]
-HEADERS = [os.path.join(CSRC, "flo_internal.h"), os.path.join(CSRC, "encode_v2_body.cuh"), os.path.join(os.path.dirname(HERE), "include", "flo_b200.h")]
+HEADERS = [os.path.join(CSRC, "flo_internal.h"), os.path.join(CSRC, "encode_v3_body.cuh"), os.path.join(os.path.dirname(HERE), "include", "flo_b200.h")]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
     "-Xcompiler", "-fPIC,-O2", "--fmad=false",

@@ -292,6 +292,7 @@ struct Layout {
     uint64_t in_bytes = 0;            // host-input arena bytes
     std::vector<uint64_t> in_off;     // byte offset of each track in the input arena
     uint64_t max_plane_elems = 0;     // C * stride of the largest frame
+    uint64_t max_group_bytes = 0;     // bytes of one interleaved sample frame of the widest track with <= 2 channels (staged ingest)
 };
 
 // worst-case bytes of one frame: 6 + C * (4 + 1 + 48 + 3 + 2 n)   (types.rs:242-267, raw payload bound)
@@ -336,6 +337,7 @@ int make_layout(const flo_track *tracks, size_t n_tracks, int format, Layout &L)
             const uint64_t cl0 = nf > 1 ? sr : last_cl0;
             const uint64_t stride = (cl0 + 15) & ~15ull;
             L.max_plane_elems = std::max(L.max_plane_elems, C * stride);
+            if (C <= 2) L.max_group_bytes = std::max<uint64_t>(L.max_group_bytes, C * (format == FLO_FMT_PCM16 ? 2 : 4));
         }
         const uint64_t fixed = FILE_HDR + 4 + 20 * nf + k.meta_len;
         stat += fixed;
@@ -408,22 +410,31 @@ static int encode_batch_impl(flo_ctx *c, const flo_track *tracks, size_t n_track
     // than one 512-thread CTA with the frame in shared memory (3.30 vs 3.69 ms per hour of 44.1 kHz stereo).
     // FLO_B200_VARIANT=512|256|128 forces a variant (tests, comparisons).
     const size_t plane_bytes = L.max_plane_elems * 2;
+    // Shared memory of a CTA: its fixed state, a work area (ingest stages of the bulk async copies, then the
+    // packer's 16 KB staging ring) and, when they fit, the sample planes.  A stage is one step of all threads.
+    const size_t WORK_MIN = (size_t)RING_WORDS * 4;
     auto share_of = [&](const EncodeVariant &v) { return v.ctas_per_sm > 1 ? c->smem_optin / v.ctas_per_sm - 1024 : c->smem_optin; };
-    auto fits = [&](const EncodeVariant &v) { return align_up(v.static_smem(), 16) + plane_bytes <= share_of(v); };
+    auto stage_of = [&](const EncodeVariant &v) { return (size_t)v.threads * (v.threads >= 512 ? 4 : 8) * (size_t)std::max<uint64_t>(L.max_group_bytes, 2); };
+    auto fits = [&](const EncodeVariant &v) { return v.static_smem() + plane_bytes + std::max(WORK_MIN, 2 * stage_of(v)) <= share_of(v); };
     const EncodeVariant *var = &encode_variant(512);
     if (fits(encode_variant(128))) var = &encode_variant(128);
     else if (fits(encode_variant(256))) var = &encode_variant(256);
     else if (host_inputs && fits(encode_variant(512))) var = &encode_variant(512);   // PCIe-bound entry: the shared-memory variant leaves HBM/L2 to the copy engines (25.3 vs 26.8 ms e2e)
     else var = &encode_variant(256);                                       // planes in L2 scratch
     if (const char *e = getenv("FLO_B200_VARIANT")) var = &encode_variant(atoi(e));
-    const size_t smem_static = align_up(var->static_smem(), 16);
+    const size_t smem_static = var->static_smem();
+    const bool planes_in_smem = fits(*var);
+    size_t work = std::max(WORK_MIN, 4 * stage_of(*var));
+    work = std::min(work, (share_of(*var) - smem_static - (planes_in_smem ? plane_bytes : 0)) & ~(size_t)127);
+    if (const char *e = getenv("FLO_B200_WORK_KB")) work = std::max(WORK_MIN, (size_t)atoi(e) * 1024);
     size_t dyn, plane_cap;
-    if (fits(*var)) { dyn = share_of(*var); plane_cap = dyn - smem_static; }
-    else { dyn = smem_static; plane_cap = 0; }                            // global (L2) planes
+    if (planes_in_smem) { dyn = share_of(*var); plane_cap = dyn - smem_static - work; }
+    else { dyn = smem_static + work; plane_cap = 0; }                     // global (L2) planes
     const int ctas_per_sm = var->ctas_per_sm;
     if (getenv("FLO_B200_DEBUG_OCC"))
         fprintf(stderr, "flo_b200: variant %d x %d, dyn smem %zu, occupancy %d\n", var->threads, ctas_per_sm, dyn, var->occupancy(dyn));
-    const int grid = (int)std::min<uint64_t>(std::max<uint64_t>(NF, 1), (uint64_t)c->sm_count * ctas_per_sm);
+    int grid = (int)std::min<uint64_t>(std::max<uint64_t>(NF, 1), (uint64_t)c->sm_count * ctas_per_sm);
+    if (const char *e = getenv("FLO_B200_GRID")) grid = std::max(1, std::min(grid, atoi(e)));   // experiments
     if ((rc = c->cres.reserve(sizeof(ChanResult) * 256ull * grid))) return rc;
     uint64_t plane_elems = 0;
     if (L.max_plane_elems * 2 > plane_cap) {
@@ -509,6 +520,8 @@ static int encode_batch_impl(flo_ctx *c, const flo_track *tracks, size_t n_track
     ep.cres = (ChanResult *)c->cres.p;
     ep.report = c->report_on ? (flo_cand_report *)c->report.p : nullptr;
     ep.smem_plane_bytes = (uint32_t)plane_cap;
+    ep.work_bytes = (uint32_t)work;
+    ep.stagger = getenv("FLO_B200_STAGGER") ? (uint32_t)atoi(getenv("FLO_B200_STAGGER")) : 0u;
 
     FinalParams fp;
     memset(&fp, 0, sizeof fp);

@@ -15,7 +15,7 @@ typedef long long i64;
 typedef uint32_t u32;
 typedef int32_t i32;
 
-#include "encode_v2_body.cuh"
+#include "encode_v3_body.cuh"
 
 }  // namespace nt128
 

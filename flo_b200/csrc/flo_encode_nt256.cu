@@ -5,7 +5,9 @@
 #include "flo_internal.h"
 
 #define FLO_VARIANT_NT 256
+#ifndef FLO_VARIANT_CTAS
 #define FLO_VARIANT_CTAS 2
+#endif
 
 namespace flo {
 namespace nt256 {
@@ -15,11 +17,11 @@ typedef long long i64;
 typedef uint32_t u32;
 typedef int32_t i32;
 
-#include "encode_v2_body.cuh"
+#include "encode_v3_body.cuh"
 
 }  // namespace nt256
 
-extern const EncodeVariant g_variant_nt256 = {256, 2, nt256::encode_static_smem, nt256::variant_configure,
+extern const EncodeVariant g_variant_nt256 = {256, FLO_VARIANT_CTAS, nt256::encode_static_smem, nt256::variant_configure,
                                               nt256::variant_launch, nt256::variant_occupancy};
 
 }  // namespace flo

@@ -72,6 +72,8 @@ struct EncodeParams {
     uint32_t *counters;               // [0] loud frames, [1] pass-3 rounds, [2] LPC sizes from the window, [3] window misses,
                                       // [4] fixed candidates evaluated exactly, [5] candidates pruned by bounds
     uint32_t smem_plane_bytes;        // bytes of dynamic shared memory available for sample planes
+    uint32_t stagger;                 // SM clocks the second half of the CTAs waits before its first frame (de-phases the CTAs that share an SM)
+    uint32_t work_bytes;              // bytes of the CTA's work area in shared memory (ingest stages / packer ring), multiple of 128, >= 16 KB
     unsigned long long *phase_cycles; // [0] ingest, [1] analysis, [2] look-back, [3] pack, [4] whole frame (SM clocks, thread 0)
 };
 

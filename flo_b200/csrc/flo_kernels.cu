@@ -1,5 +1,5 @@
 // flo_kernels.cu -- setup / TOC / CRC / header kernels and the variant table of the lossless ALPC encode path
-// (the frame-encode kernel itself is encode_v2_body.cuh, built three times by flo_encode_nt*.cu).
+// (the frame-encode kernel itself is encode_v3_body.cuh, built three times by flo_encode_nt*.cu).
 //
 // One persistent CTA per SM takes frames from a ticket counter (ticket order ==
 // global frame order, which makes the decoupled look-back below deadlock free),

@@ -10,7 +10,8 @@ secs=int(sys.argv[1]) if len(sys.argv)>1 else 1184
 pcm=synth_torch.synth_pcm16_long(secs*SR,CH,SR,0xF12,"multitone",64,"cuda")
 x=pcm.float()*(1/32768)
 n=[x.numel()]; bound=ctx.output_bound(n,[SR],[CH]); out=torch.empty(bound,dtype=torch.uint8,device="cuda")
-for lv in (0,2,5,9):
+levels=[int(v) for v in sys.argv[2].split(',')] if len(sys.argv)>2 else (0,2,5,9)
+for lv in levels:
     for _ in range(3): ctx.encode_batch_device([x.data_ptr()],n,[SR],[CH],[16],out.data_ptr(),bound,level=lv)
     t=ctx.last_timing(); c=ctx.last_counters()["phase_clocks"]; f=secs
     print(f"level {lv}: kernel {t['encode_ms']:.3f} ms; per-frame clocks: " + ", ".join(f"{k} {v/f:.0f}" for k,v in c.items()))
