@@ -19,10 +19,21 @@
 constexpr int NT = FLO_VARIANT_NT;
 constexpr int NWARP = NT / 32;
 
+#ifndef FLO_PAIR_BS
+#define FLO_PAIR_BS 4         // samples per block of the two-order FIR sweeps (independent chains = 2 x this)
+#endif
 #ifdef FLO_PHASE_CLOCKS
 #define PH(...) __VA_ARGS__
 #else
 #define PH(...)
+#endif
+#ifdef FLO_LEV_CLOCKS         // experiment: Levinson sub-steps on the pack slots 5..7 and 14
+#define LV(...) __VA_ARGS__
+#define LEVC 1
+__device__ unsigned long long *g_lev_phase;
+#else
+#define LV(...)
+#define LEVC 0
 #endif
 
 // ----------------------------------------------------------------------------
@@ -32,6 +43,7 @@ constexpr int GROUP = 2;              // channels analysed jointly (stereo = one
 constexpr int NLPC = MAXORD - 4;      // LPC orders 5..12
 constexpr int MAX_STAGES = 4;         // bulk-copy stages of the ingest ring
 constexpr int SPT = NT >= 512 ? 4 : 8;   // sample frames per thread per ingest step
+constexpr int WRING = 512;            // words of one warp's staging ring in the packer
 
 // candidate states
 constexpr int CS_ABSENT = 0, CS_EXACT = 1, CS_BOUNDED = 2;
@@ -62,6 +74,7 @@ struct ChanState {
     u64 l_t0[NLPC], l_t1[NLPC];
     // candidates: 0 raw, 1..5 fixed 0..4, 6..13 lpc 5..12
     i32 cand_state[NCAND];
+    i32 cand_src[NCAND];              // where the exact size came from: 0 pass 3 (partS), 1 / 2 pass 2 window t0 / t1 (partT)
     i32 cand_k[NCAND];
     i64 cand_size[NCAND];             // exact bytes when CS_EXACT
     u64 cand_sumabs[NCAND];
@@ -76,7 +89,7 @@ struct ChanState {
 struct Smem {
     ChanState cs[GROUP];
     i32 wcoef[MAXORD];                // winner's coefficients while packing
-    double wqd[MAXORD];
+    double wqd[GROUP][MAXORD];
     u32 scan_warp[2][NWARP];
     u32 cnt[8];                       // analysis counters of this CTA (flushed at kernel end)
     u32 g;                            // current global frame
@@ -86,6 +99,12 @@ struct Smem {
     u64 frame_excl;                   // exclusive prefix of frame sizes
     unsigned long long bar_full[MAX_STAGES];   // mbarriers of the ingest stages
     u32 headw[NT];                    // packer: first (shared) word of each thread's chunk stream
+    // per-region (= per warp of the channel) partial sums of the analysis passes: the packer's regions start at
+    // bit offsets that follow from them, so the warps of a channel pack independently of each other
+    u64 partA[GROUP][NCAND][NWARP];   // sum|r| per region (fixed: pass 1, LPC: pass 2)
+    u64 partT[GROUP][NLPC][2][NWARP]; // pass 2: sum(w >> j0), sum(w >> (j0 + 1)) per region
+    u64 partS[GROUP][NCAND][NWARP];   // pass 3: exact sum(w >> j) per region
+    u32 edge[GROUP][NWARP + 1];       // packer: bits of the words shared by two regions, by boundary
 };
 // dynamic shared memory: Smem | work area (ingest stages, then the packer's staging ring) | sample planes
 constexpr size_t SMEM_HDR = (sizeof(Smem) + 127) & ~size_t(127);
@@ -195,6 +214,7 @@ __device__ __forceinline__ void rice_bounds(u64 sum_abs, u32 n, int k, i64 &lb, 
 template <int P>
 __device__ void levinson_all_orders(ChanState &cs) {      // called by a full warp
     const int lane = threadIdx.x & 31;
+    LV(const long long l0 = clock64();)
     if (lane < NLPC) { cs.lpc_ok[lane] = 0; cs.lpc_shift[lane] = 0; cs.lpc_j0[lane] = 0; }
     __syncwarp();
     // (1) the recursion itself is sequential: lane 0.  Unquantised coefficients of every order >= 5 are
@@ -231,6 +251,7 @@ __device__ void levinson_all_orders(ChanState &cs) {      // called by a full wa
         }
     }
     __syncwarp();
+    LV(const long long l1 = clock64();)
     // (2) per order (lane t = order - 5): max |a|, shift, and the size-window guess
     if (lane < P - 4 && cs.lpc_ok[lane] == 2) {
         const int o = 5 + lane;
@@ -261,6 +282,7 @@ __device__ void levinson_all_orders(ChanState &cs) {      // called by a full wa
         cs.lpc_ok[lane] = ok;
     }
     __syncwarp();
+    LV(const long long l2 = clock64();)
     // (3) quantise every (order, j) pair in parallel (lpc.rs:263-273); taps of orders that were not reached are
     //     zero so that the FIR sweeps can run them blindly (their statistics are ignored)
     for (int item = lane; item < (P - 4) * P; item += 32) {
@@ -281,6 +303,7 @@ __device__ void levinson_all_orders(ChanState &cs) {      // called by a full wa
         }
     }
     __syncwarp();
+    LV(if (threadIdx.x == 0) { const long long l3 = clock64(); atomicAdd(g_lev_phase + 5, (u64)(l1 - l0)); atomicAdd(g_lev_phase + 6, (u64)(l2 - l1)); atomicAdd(g_lev_phase + 7, (u64)(l3 - l2)); })
 }
 
 // ----------------------------------------------------------------------------
@@ -441,20 +464,28 @@ __device__ __forceinline__ i32 sample_at(const ChanState &cs, int i) {
     const i32 b = cs.pb[i];
     return cs.msmode == 1 ? a + b : a - b;
 }
+// The lane's sample and its MAXORD predecessors, fetched with independent loads (one L2 round trip instead
+// of one per tap): w[t] = s[i - t], zero outside the channel.
+struct LaneWin { i32 w[MAXORD + 1]; };
+__device__ __forceinline__ void lane_window(const ChanState &cs, int i, LaneWin &win) {
+#pragma unroll
+    for (int t = 0; t <= MAXORD; t++) win.w[t] = sample_at(cs, i - t);
+}
 // fixed_predictor_residuals (lpc.rs:301-359) at index i: the min(o, i)-th finite difference
-__device__ __noinline__ i32 fixed_residual_at(const ChanState &cs, int o, int i) {
+__device__ __forceinline__ i32 fixed_residual_at(const LaneWin &win, int o, int i) {
+    const u32 w0 = (u32)win.w[0], w1 = (u32)win.w[1], w2 = (u32)win.w[2], w3 = (u32)win.w[3], w4 = (u32)win.w[4];
     const int oo = o < i ? o : i;
-    const i32 binom[5][5] = {{1, 0, 0, 0, 0}, {1, -1, 0, 0, 0}, {1, -2, 1, 0, 0}, {1, -3, 3, -1, 0}, {1, -4, 6, -4, 1}};
-    u32 r = 0;
-    for (int t = 0; t <= oo; t++) r += (u32)binom[oo][t] * (u32)sample_at(cs, i - t);
-    return (i32)r;
+    const u32 d1 = w0 - w1, d2 = w0 - 2u * w1 + w2, d3 = w0 - 3u * w1 + 3u * w2 - w3, d4 = w0 - 4u * w1 + 6u * w2 - 4u * w3 + w4;
+    return (i32)(oo == 0 ? w0 : oo == 1 ? d1 : oo == 2 ? d2 : oo == 3 ? d3 : d4);
 }
 // calc_residuals_int (lpc.rs:279-298) at index i, in the reference's own i64 arithmetic
-__device__ __noinline__ i32 lpc_residual_at(const ChanState &cs, int o, int i) {
-    const i32 x = sample_at(cs, i);
+__device__ __forceinline__ i32 lpc_residual_at(const ChanState &cs, const LaneWin &win, int o, int i) {
+    const i32 x = win.w[0];
     if (i < o) return x;
     i64 pred = 0;
-    for (int t = 0; t < o; t++) pred += (i64)cs.qc[o - 5][t] * (i64)sample_at(cs, i - 1 - t);
+#pragma unroll
+    for (int t = 0; t < MAXORD; t++)
+        if (t < o) pred += (i64)cs.qc[o - 5][t] * (i64)win.w[1 + t];
     pred >>= cs.lpc_shift[o - 5];
     return (i32)((u32)x - (u32)(i32)pred);
 }
@@ -467,34 +498,46 @@ __device__ __noinline__ i32 lpc_residual_at(const ChanState &cs, int o, int i) {
 // 0..15) and the < 16 samples behind the last full chunk (lanes 16..30) are added by the channel's
 // last warp, one lane per sample, through the scalar functions above.
 // ----------------------------------------------------------------------------
+// Region of warp wi (of the W warps of a channel) over the full chunks 1 .. nfull-1: [a, b).  The packer uses
+// the same regions; region 0 additionally owns chunk 0 and region W-1 the partial chunk behind the last full one.
+__device__ __forceinline__ void region_chunks(int nfull, int W, int wi, int &a, int &b) {
+    const int m = nfull > 1 ? nfull - 1 : 0;
+    const int R = (m + W - 1) / W;
+    a = 1 + wi * R;
+    b = min(1 + (wi + 1) * R, nfull);
+    if (a > b) a = b;
+}
+
 template <int NH, class Reset, class Body, class Tail, class Flush>
 __device__ __forceinline__ void for_chunks(const Smem &s, int nch, Reset &&reset, Body &&body, Tail &&tailfn, Flush &&flush) {
     const int wid = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int c = nch == 2 ? (wid & 1) : 0;
     const int wi = nch == 2 ? (wid >> 1) : wid;
-    const int nthr = nch == 2 ? NT / 2 : NT;
-    const int ti = wi * 32 + lane;
-    const bool tail_warp = wi == nthr / 32 - 1;
+    const int W = nch == 2 ? NWARP / 2 : NWARP;
     const ChanState &cs = s.cs[c];
     const int nfull = cs.nfull;
-    int base = 1;
-    bool edges = true;
+    int ca, cb;
+    region_chunks(nfull, W, wi, ca, cb);
+    int base = ca;
     do {
         reset();
-        const int end = min(nfull, base + nthr * 64);
-        for (int chunk = base + ti; chunk < end; chunk += nthr) {
+        const int end = min(cb, base + 32 * 64);
+        for (int chunk = base + lane; chunk < end; chunk += 32) {
             i32 x[NH + CH];
             load_chunk<NH, true>(cs, chunk * CH, x);
             body(c, chunk, x);
         }
-        if (edges && tail_warp) {
-            if (lane < 16) { if (nfull >= 1) tailfn(c, lane); }
-            else if (lane - 16 < cs.tail) tailfn(c, nfull * CH + lane - 16);
+        if (end == cb) {
+            // chunk 0 belongs to region 0 (lanes 0..15 of its warp), the samples behind the last full chunk to
+            // region W - 1 (lanes 16..30 of its warp): they join the region's last flush
+            int i = -1;
+            if (wi == 0 && lane < 16 && nfull >= 1) i = lane;
+            if (wi == W - 1 && lane >= 16 && lane - 16 < cs.tail) i = nfull * CH + lane - 16;
+            if (i >= 0) { LaneWin win; lane_window(cs, i, win); tailfn(c, i, win); }
         }
-        edges = false;
-        flush(c);
+        flush(c, wi);
         base = end;
-    } while (base < nfull);
+    } while (base < cb);
 }
 
 // ---- pass 1: fixed-predictor statistics (sum|r|, OR|r|) for orders 0..NF-1 + autocorrelation (lpc.rs:213-221) ----
@@ -538,26 +581,25 @@ __device__ void pass1(Smem &s, int nch) {
                 }
             });
         },
-        [&](int c, int i) {
-            const ChanState &cs = s.cs[c];
+        [&](int c, int i, const LaneWin &win) {
 #pragma unroll
             for (int o = 0; o < NF; o++) {
-                const u32 a = (u32)abs(fixed_residual_at(cs, o, i));
+                const u32 a = (u32)abs(fixed_residual_at(win, o, i));
                 fsum[o] += a; forr[o] |= a;
             }
             if constexpr (P > 0) {
-                const double xi = (double)sample_at(cs, i);
+                const double xi = (double)win.w[0];
 #pragma unroll
-                for (int l = 0; l <= P; l++) acc[l] = __fma_rn(xi, (double)sample_at(cs, i - l), acc[l]);
+                for (int l = 0; l <= P; l++) acc[l] = __fma_rn(xi, (double)win.w[l], acc[l]);
             }
         },
-        [&](int c) {
+        [&](int c, int region) {
             ChanState &cs = s.cs[c];
 #pragma unroll
             for (int o = 0; o < NF; o++) {
                 const u64 t = warp_sum64((u64)fsum[o]);
                 const u32 r = __reduce_or_sync(0xffffffffu, forr[o]);
-                if (lane == 0) { atomic_add64(&cs.fix_sum[o], t); atomicOr(&cs.fix_or[o], r); }
+                if (lane == 0) { atomic_add64(&cs.fix_sum[o], t); atomicOr(&cs.fix_or[o], r); atomic_add64(&s.partA[c][1 + o][region], t); }
             }
             if constexpr (P > 0) {
 #pragma unroll
@@ -578,8 +620,13 @@ struct Sweeps {
     static constexpr int NO = HI - LO + 1;
     static __device__ __forceinline__ void run(const ChanState &cs, const i32 (&x)[NH + CH], LpcStat *st /* by order - LO0 */, int lo0) {
         if constexpr (LO <= HI) {
+#ifdef FLO_SINGLE_SWEEPS
+            constexpr int OA = HI, OB = 0;
+            constexpr int BS = 4;
+#else
             constexpr int OA = HI, OB = LO < HI ? LO : 0;
-            constexpr int BS = (OA + OB > 14) ? 2 : 4;
+            constexpr int BS = FLO_PAIR_BS;
+#endif
             const bool oka = cs.lpc_ok[OA - 5] != 0, okb = OB > 0 && cs.lpc_ok[(OB > 0 ? OB : 5) - 5] != 0;
             if (oka || okb) {
                 LpcStat a = st[OA - lo0], b = st[(OB > 0 ? OB : OA) - lo0];
@@ -604,7 +651,11 @@ struct Sweeps {
                 st[OA - lo0] = a;
                 if constexpr (OB > 0) st[OB - lo0] = b;
             }
+#ifdef FLO_SINGLE_SWEEPS
+            Sweeps<NH, LO, HI - 1>::run(cs, x, st, lo0);
+#else
             Sweeps<NH, LO + 1, HI - 1>::run(cs, x, st, lo0);
+#endif
         }
     }
 };
@@ -626,19 +677,19 @@ __device__ void pass2_range(Smem &s, int nch) {
         [&](int c, int chunk, const i32 (&x)[NH + CH]) {
             Sweeps<NH, LO, HI>::run(s.cs[c], x, st, LO);
         },
-        [&](int c, int i) {
+        [&](int c, int i, const LaneWin &win) {
             const ChanState &cs = s.cs[c];
 #pragma unroll
             for (int O = LO; O <= HI; O++) {
                 if (cs.lpc_ok[O - 5]) {
-                    const i32 r = lpc_residual_at(cs, O, i);
+                    const i32 r = lpc_residual_at(cs, win, O, i);
                     const u32 a = (u32)abs(r);
                     const u32 ws = (a + (u32)(r >> 31)) >> cs.lpc_j0[O - 5];
                     st[O - LO].sum += a; st[O - LO].orr |= a; st[O - LO].t0 += ws; st[O - LO].t1 += ws >> 1;
                 }
             }
         },
-        [&](int c) {
+        [&](int c, int region) {
             ChanState &cs = s.cs[c];
 #pragma unroll
             for (int i = 0; i < NO; i++) {
@@ -647,6 +698,8 @@ __device__ void pass2_range(Smem &s, int nch) {
                 if (lane == 0) {
                     atomic_add64(&cs.l_sum[LO - 5 + i], a); atomic_add64(&cs.l_t0[LO - 5 + i], b); atomic_add64(&cs.l_t1[LO - 5 + i], d);
                     atomicOr(&cs.l_or[LO - 5 + i], r);
+                    atomic_add64(&s.partA[c][6 + LO - 5 + i][region], a);
+                    atomic_add64(&s.partT[c][LO - 5 + i][0][region], b); atomic_add64(&s.partT[c][LO - 5 + i][1][region], d);
                 }
             }
         });
@@ -743,14 +796,14 @@ __device__ void pass3(Smem &s, int nch) {
             }
             S += acc;
         },
-        [&](int c, int i) {
+        [&](int c, int i, const LaneWin &win) {
             const ChanState &cs = s.cs[c];
             const int cand = cs.ex_cand;
             if (cand < 0) return;
             if (cs.ex_fixed) {
 #pragma unroll
                 for (int o = 0; o < NF; o++) {
-                    const i32 r = fixed_residual_at(cs, o, i);
+                    const i32 r = fixed_residual_at(win, o, i);
                     S5[o] += ((u32)abs(r) + (u32)(r >> 31)) >> max(cs.cand_k[1 + o] - 1, 0);
                 }
                 return;
@@ -758,21 +811,24 @@ __device__ void pass3(Smem &s, int nch) {
             const int k = cs.cand_k[cand];
             const int jj = k >= 1 ? k - 1 : 0;
             const int mode = cand - 1;
-            const i32 r = mode <= 4 ? fixed_residual_at(cs, mode, i) : lpc_residual_at(cs, mode, i);
+            const i32 r = mode <= 4 ? fixed_residual_at(win, mode, i) : lpc_residual_at(cs, win, mode, i);
             const u32 a = (u32)abs(r);
             mx = max(mx, a);
             S += (a + (u32)(r >> 31)) >> jj;
         },
-        [&](int c) {
+        [&](int c, int region) {
             ChanState &cs = s.cs[c];
             const u64 t = warp_sum64(S);
             const u32 m = __reduce_max_sync(0xffffffffu, mx);
-            if (lane == 0 && cs.ex_cand >= 0) { atomic_add64(&cs.ex_s, t); atomicMax(&cs.ex_max, m); }
+            if (lane == 0 && cs.ex_cand >= 0) {
+                atomic_add64(&cs.ex_s, t); atomicMax(&cs.ex_max, m);
+                if (!cs.ex_fixed) atomic_add64(&s.partS[c][cs.ex_cand][region], t);
+            }
             if (cs.ex_fixed) {
 #pragma unroll
                 for (int o = 0; o < NF; o++) {
                     const u64 t5 = warp_sum64((u64)S5[o]);
-                    if (lane == 0) atomic_add64(&cs.ex_s5[o], t5);
+                    if (lane == 0 && (cs.ex_fixed >> o & 1)) { atomic_add64(&cs.ex_s5[o], t5); atomic_add64(&s.partS[c][1 + o][region], t5); }
                 }
             }
         });
@@ -801,6 +857,7 @@ __device__ void after_pass1_warp(ChanState &cs, int fmax, bool lpc_on) {
             sumabs = cs.fix_sum[o];
         }
         cs.cand_state[lane] = state; cs.cand_k[lane] = k; cs.cand_size[lane] = size; cs.cand_sumabs[lane] = sumabs;
+        cs.cand_src[lane] = 0;
     }
     if (lane < NLPC) cs.lpc_ok[lane] = 0;
     __syncwarp();
@@ -828,6 +885,7 @@ __device__ void after_pass2_warp(ChanState &cs, int P, u32 *counters) {
             const int jj = k >= 1 ? k - 1 : 0;
             if (bl <= 19 && (jj == cs.lpc_j0[i] || jj == cs.lpc_j0[i] + 1)) {
                 const u64 S = jj == cs.lpc_j0[i] ? cs.l_t0[i] : cs.l_t1[i];
+                cs.cand_src[lane] = jj == cs.lpc_j0[i] ? 1 : 2;
                 cs.cand_state[lane] = CS_EXACT;
                 cs.cand_size[lane] = rice_bytes(S, cs.l_sum[i], n, k);
                 hit = true;
@@ -1032,58 +1090,93 @@ __device__ __noinline__ void emit_slow(u32 *ring, u32 wbase, const u32 *u, int n
 
 __device__ __forceinline__ u32 bswap32(u32 v) { return __byte_perm(v, 0, 0x0123); }
 
-// Write `ng` complete groups of four ring words (slots 0 .. 4 ng) to the output and clear them; then thread 0
-// moves the group behind them (complete words that do not fill a group yet + the partial word) to slot 0.
-// Group g is the 16 bytes at abase + 4 wbase + 16 g; only bytes inside [lo, hi) belong to this payload.
-__device__ __forceinline__ void flush_groups(u32 *ring, uint8_t *obase, u64 abase, u64 lo, u64 hi, u32 wbase, u32 ng) {
+// What a warp needs to know about the bytes it may write: [lo, hi) are the bytes of the words it owns alone;
+// the word index `ehw` / `etw` (when `eh` / `et`) is shared with the region in front / behind, and its bits are
+// collected in the CTA's edge accumulators instead (shared addresses ehp / etp).
+struct RegionOut {
+    uint8_t *obase;
+    u64 abase, lo, hi;
+    u32 ehw, etw, ehp, etp;
+    bool eh, et;
+};
+__device__ __forceinline__ void store_word_masked(const RegionOut &o, u32 w, u32 v) {
+    const u64 a = o.abase + 4ull * w;
+#pragma unroll
+    for (int b = 0; b < 4; b++)
+        if (a + b >= o.lo && a + b < o.hi) o.obase[a + b] = (uint8_t)(v >> (24 - 8 * b));
+    if (o.eh && w == o.ehw && v) atom_or_shared(o.ehp, v);
+    if (o.et && w == o.etw && v) atom_or_shared(o.etp, v);
+}
+// Write `ng` complete groups of four ring words (slots 0 .. 4 ng) of this warp's ring to the output and clear
+// them; then lane 0 moves the group behind them (complete words that do not fill a group yet + the partial
+// word) to slot 0.  Group g is the 16 bytes at abase + 4 wbase + 16 g.
+__device__ __forceinline__ void flush_groups(u32 *ring, const RegionOut &o, u32 wbase, u32 ng) {
+    const u32 lane = threadIdx.x & 31;
     uint4 *r4 = reinterpret_cast<uint4 *>(ring);
-    for (u32 g = threadIdx.x; g < ng; g += NT) {
+    for (u32 g = lane; g < ng; g += 32) {
         const uint4 v = r4[g];
         r4[g] = make_uint4(0, 0, 0, 0);
-        const u64 a = abase + 4ull * wbase + 16ull * g;
-        if (a >= lo && a + 16 <= hi) {
-            *reinterpret_cast<uint4 *>(obase + a) = make_uint4(bswap32(v.x), bswap32(v.y), bswap32(v.z), bswap32(v.w));
+        const u64 a = o.abase + 4ull * wbase + 16ull * g;
+        if (a >= o.lo && a + 16 <= o.hi) {
+            *reinterpret_cast<uint4 *>(o.obase + a) = make_uint4(bswap32(v.x), bswap32(v.y), bswap32(v.z), bswap32(v.w));
         } else {
-            const u32 wv[4] = {v.x, v.y, v.z, v.w};
-#pragma unroll
-            for (int q = 0; q < 4; q++)
-#pragma unroll
-                for (int b = 0; b < 4; b++) {
-                    const u64 ab = a + 4 * q + b;
-                    if (ab >= lo && ab < hi) obase[ab] = (uint8_t)(wv[q] >> (24 - 8 * b));
-                }
+            store_word_masked(o, wbase + 4 * g, v.x); store_word_masked(o, wbase + 4 * g + 1, v.y);
+            store_word_masked(o, wbase + 4 * g + 2, v.z); store_word_masked(o, wbase + 4 * g + 3, v.w);
         }
     }
-    if (threadIdx.x == 0 && ng > 0) {
+    if (lane == 0 && ng > 0) {
         const uint4 c = r4[ng];
         r4[ng] = make_uint4(0, 0, 0, 0);
         r4[0] = c;
     }
 }
 
-// Pack one channel's residual payload at byte offset `pos` (relative to obase, which is 16-byte
-// aligned) -- encode_i32 / BitWriter (rice.rs:84-92, 162-208) or encode_raw (encoder.rs:220-226).
+// samples of region wi: its full chunks, chunk 0 for region 0, the partial chunk for region W - 1
+__device__ __forceinline__ u32 region_samples(int n, int W, int wi) {
+    const int nfull = n / CH, tail = n % CH;
+    int ca, cb;
+    region_chunks(nfull, W, wi, ca, cb);
+    return (u32)(cb - ca) * CH + ((wi == 0 && nfull >= 1) ? (u32)CH : 0u) + (wi == W - 1 ? (u32)tail : 0u);
+}
+
+// Pack the residual payload of region wi (of W) of one channel; called by one warp.  The payload starts at
+// byte offset `pos` (relative to obase, which is 16-byte aligned) -- encode_i32 / BitWriter (rice.rs:84-92,
+// 162-208) or encode_raw (encoder.rs:220-226).  The region's bit offset inside the payload is the sum of the
+// bit counts of the regions in front (cr.regbits, from the analysis passes); no block-wide step is needed.
 template <int P>
-__device__ void pack_channel(Smem &s, u32 *ring, const ChanState &cs, const ChanResult &cr, uint8_t *obase, u64 pos, u32 *err,
-                             unsigned long long *phase) {
-    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
-    const int n = cs.n;
+__device__ void pack_region(Smem &s, u32 *ring, const ChanState &cs, int cq, const ChanResult &cr, uint8_t *obase, u64 pos, int wi, int W,
+                            u32 *err) {
+    const int lane = threadIdx.x & 31;
+    const int n = cs.n, nfull = n / CH, tail = n % CH;
     const int mode = cr.kind == 0 ? 13 : cr.order;
     const bool raw = cr.kind == 0;
     const int k = cr.k;
-    const u64 abase = pos & ~15ull;
-    const u64 lo = pos, hi = pos + cr.nbytes;
-    u64 bitpos = (pos & 15ull) * 8ull;
-    u32 wbase = 0;                                     // ring slot 0 <-> stream word wbase (multiple of 4)
-    const u32 ring_addr = smem_u32(ring), head_addr = smem_u32(&s.headw[tid]);
-    const int per_sc = NT * CH;
-    const int nsc = (n + per_sc - 1) / per_sc;
-    const double *qd = s.wqd;
-    for (int sc = 0; sc < nsc; sc++) {
-        PH(const long long pk0 = clock64();)
-        const int i0 = sc * per_sc + tid * CH;
-        const bool last = sc == nsc - 1;               // only the last round has short or absent chunks
-        const int nv = last ? max(0, min(CH, n - i0)) : CH;
+    u64 bitstart = (pos & 15ull) * 8ull;
+    for (int v = 0; v < wi; v++) bitstart += cr.regbits[v];
+    const u64 bits = cr.regbits[wi];
+    if (bits == 0) return;
+    const u64 bitend = bitstart + bits;
+    RegionOut o;
+    o.obase = obase;
+    o.abase = pos & ~15ull;
+    o.eh = wi > 0 && (bitstart & 31) != 0;
+    o.et = wi < W - 1 && (bitend & 31) != 0;
+    o.ehw = (u32)(bitstart >> 5); o.etw = (u32)(bitend >> 5);
+    o.ehp = smem_u32(&s.edge[cq][wi]); o.etp = smem_u32(&s.edge[cq][wi + 1]);
+    o.lo = wi == 0 ? pos : o.abase + 4ull * ((bitstart + 31) >> 5);
+    o.hi = wi == W - 1 ? pos + cr.nbytes : o.abase + 4ull * (bitend >> 5);
+    int ca, cb;
+    region_chunks(nfull, W, wi, ca, cb);
+    const int cstart = (wi == 0 && nfull >= 1) ? 0 : ca;
+    const int cend = cb + ((wi == W - 1 && tail > 0) ? 1 : 0);
+    const double *qd = s.wqd[cq];
+    const u32 ring_addr = smem_u32(ring), head_addr = smem_u32(&s.headw[threadIdx.x]);
+    u64 bitpos = bitstart;
+    u32 wbase = (u32)(bitstart >> 5) & ~3u;            // ring slot 0 <-> stream word wbase (multiple of 4)
+    for (int base = cstart; base < cend; base += 32) {
+        const int chunk = base + lane;
+        const int i0 = chunk * CH;
+        const int nv = chunk < cend ? (chunk == nfull ? tail : CH) : 0;
         u32 u[CH];
         u32 tb = 0;
         bool fast = true;
@@ -1106,7 +1199,7 @@ __device__ void pack_channel(Smem &s, u32 *ring, const ChanState &cs, const Chan
             }
             if (raw) {
                 tb = 16u * (u32)nv;
-            } else if (!last) {
+            } else if (nv == CH) {
                 u32 qs = 0, orr = 0;
 #pragma unroll
                 for (int j = 0; j < CH; j += 2) { qs += (u[j] >> k) + (u[j + 1] >> k); orr |= u[j] | u[j + 1]; }
@@ -1120,89 +1213,63 @@ __device__ void pack_channel(Smem &s, u32 *ring, const ChanState &cs, const Chan
                 fast = (orr >> k) <= 15u;
             }
         }
-        PH(const long long pk1 = clock64();)
-        // block exclusive scan of the chunk bit counts: warp scan, one barrier, then every warp scans the
-        // warp totals itself.  The totals are double buffered by round parity; this barrier also orders the
-        // previous round's ring flush (and carry) before this round's ring writes.
+        // warp exclusive scan of the chunk bit counts
         u32 inc = tb;
 #pragma unroll
-        for (int o = 1; o < 32; o <<= 1) {
-            u32 t = __shfl_up_sync(0xffffffffu, inc, o);
-            if (lane >= o) inc += t;
+        for (int d = 1; d < 32; d <<= 1) {
+            const u32 t = __shfl_up_sync(0xffffffffu, inc, d);
+            if (lane >= d) inc += t;
         }
-        u32 *tot = s.scan_warp[sc & 1];
-        if (lane == 31) tot[wid] = inc;
-        __syncthreads();
-        u32 wv = lane < NWARP ? tot[lane] : 0;
-        u32 wincl = wv;
-#pragma unroll
-        for (int o = 1; o < NWARP; o <<= 1) {
-            u32 t = __shfl_up_sync(0xffffffffu, wincl, o);
-            if (lane >= o) wincl += t;
-        }
-        const u32 warp_excl = __shfl_sync(0xffffffffu, wincl - wv, wid);
-        const u32 scan_total = __shfl_sync(0xffffffffu, wincl, NWARP - 1);
-        PH(const long long pk2 = clock64();)
-        const u64 start = bitpos + warp_excl + (inc - tb);
-        const u64 end_sc = bitpos + scan_total;
-        const u32 wlast = (u32)((end_sc + 31) >> 5);
-        if (wlast - wbase <= (u32)RING_WORDS - 4u) {        // (the group behind the last complete one is moved, too)
-            // common case: the whole round fits the staging ring
+        const u32 total = __shfl_sync(0xffffffffu, inc, 31);
+        const u64 start = bitpos + (inc - tb);
+        const u64 end_r = bitpos + total;
+        const u32 wlast = (u32)((end_r + 31) >> 5);
+        if (wlast - wbase <= (u32)WRING - 4u) {        // (the group behind the last complete one is moved, too)
             if (nv > 0) {
                 if (fast) {
-                    if (!last) emit_fast<false>(ring_addr, wbase, head_addr, u, CH, k, raw, start);
+                    if (nv == CH) emit_fast<false>(ring_addr, wbase, head_addr, u, CH, k, raw, start);
                     else emit_fast<true>(ring_addr, wbase, head_addr, u, nv, k, raw, start);
                 } else {
                     u32 uc[CH];                    // (a copy: keeps u itself in registers on the common path)
 #pragma unroll
                     for (int j = 0; j < CH; j++) uc[j] = u[j];
-                    emit_slow(ring, wbase, uc, nv, k, raw, start, wbase, wbase + RING_WORDS - 4u);
+                    emit_slow(ring, wbase, uc, nv, k, raw, start, wbase, wbase + WRING - 4u);
                 }
             }
-            __syncthreads();
-            PH(if (tid == 0) { const long long pk3 = clock64(); atomicAdd(phase + 5, (u64)(pk1 - pk0)); atomicAdd(phase + 6, (u64)(pk2 - pk1)); atomicAdd(phase + 7, (u64)(pk3 - pk2)); })
-            PH(const long long pk4 = clock64();)
-            const u32 ng = ((u32)(end_sc >> 5) - wbase) >> 2;
-            flush_groups(ring, obase, abase, lo, hi, wbase, ng);
+            __syncwarp();
+            const u32 ng = ((u32)(end_r >> 5) - wbase) >> 2;
+            flush_groups(ring, o, wbase, ng);
             wbase += 4u * ng;
-            PH(if (tid == 0) atomicAdd(phase + 14, (u64)(clock64() - pk4));)
+            __syncwarp();
         } else {
             u32 uc[CH];
 #pragma unroll
             for (int j = 0; j < CH; j++) uc[j] = u[j];
             for (;;) {
-                const u32 whi = wbase + RING_WORDS - 4u;
+                const u32 whi = wbase + WRING - 4u;
                 if (nv > 0) emit_slow(ring, wbase, uc, nv, k, raw, start, wbase, whi);
-                __syncthreads();
-                const u32 wend = min(whi, (u32)(end_sc >> 5));
+                __syncwarp();
+                const u32 wend = min(whi, (u32)(end_r >> 5));
                 const u32 ng = (wend - wbase) >> 2;
-                flush_groups(ring, obase, abase, lo, hi, wbase, ng);
+                flush_groups(ring, o, wbase, ng);
                 wbase += 4u * ng;
-                const bool done = whi >= wlast;
-                __syncthreads();
-                if (done) break;
+                __syncwarp();
+                if (whi >= wlast) break;
             }
         }
-        bitpos = end_sc;
+        bitpos = end_r;
     }
-    __syncthreads();
     {
         // what is left: at most three complete words and the partial one
         const u32 wfin = (u32)((bitpos + 31) >> 5);
-        if (wbase + (u32)tid < wfin) {
-            const u32 v = ring[tid];
-            ring[tid] = 0;
-            const u64 a = abase + 4ull * (wbase + (u32)tid);
-#pragma unroll
-            for (int b = 0; b < 4; b++)
-                if (a + b >= lo && a + b < hi) obase[a + b] = (uint8_t)(v >> (24 - 8 * b));
+        if (wbase + (u32)lane < wfin) {
+            const u32 v = ring[lane];
+            ring[lane] = 0;
+            store_word_masked(o, wbase + (u32)lane, v);
         }
     }
-    if (tid == 0) {
-        const u64 bits = bitpos - (pos & 15ull) * 8ull;
-        if (((bits + 7) >> 3) != (u64)cr.nbytes) atomicExch(err, 0xBAD00001u);
-    }
-    __syncthreads();
+    if (lane == 0 && bitpos != bitend) atomicExch(err, 0xBAD00003u);
+    __syncwarp();
 }
 
 // ----------------------------------------------------------------------------
@@ -1341,7 +1408,8 @@ __device__ __forceinline__ u32 ingest_staged(Smem &s, unsigned char *work, u32 n
     constexpr u32 BT = SPT * C * (u32)sizeof(T);       // bytes per thread and step
     constexpr u32 STAGE = NT * BT;
     const int tid = threadIdx.x;
-    const u32 ngrp = nf / SPT;
+    u32 ngrp = nf / SPT;
+    if (BT % 16 != 0) ngrp &= ~1u;                     // bulk copies move multiples of 16 bytes
     const u32 nsteps = (ngrp + NT - 1) / NT;
     const u32 work_addr = smem_u32(work), bar0 = smem_u32(&s.bar_full[0]);
     auto issue = [&](u32 k) {
@@ -1451,6 +1519,7 @@ __global__ void __launch_bounds__(NT, FLO_VARIANT_CTAS) k_encode_frames(const En
     u32 *ring = reinterpret_cast<u32 *>(work);
     int16_t *smem_planes = reinterpret_cast<int16_t *>(work + p.work_bytes);
     const int tid = threadIdx.x;
+    LV(g_lev_phase = p.phase_cycles;)
     if (tid < 8) s.cnt[tid] = 0;
     if (tid == 0) {
         for (int i = 0; i < MAX_STAGES; i++) mbar_init(smem_u32(&s.bar_full[i]), 1);
@@ -1503,9 +1572,9 @@ __global__ void __launch_bounds__(NT, FLO_VARIANT_CTAS) k_encode_frames(const En
             ingest_frame<float>(s, work, p.work_bytes, reinterpret_cast<const float *>(tr.samples) + start, len, C, planes, stride, tma_phase);
         PH(const long long tcB = clock64();)
         // the work area becomes the packer's staging ring: all zero
-        for (int i = tid; i < RING_WORDS / 4; i += NT) reinterpret_cast<uint4 *>(ring)[i] = make_uint4(0, 0, 0, 0);
+        for (int i = tid; i < NWARP * WRING / 4; i += NT) reinterpret_cast<uint4 *>(ring)[i] = make_uint4(0, 0, 0, 0);
         __syncthreads();
-        PH(if (tid == 0) { atomicAdd(p.phase_cycles + 12, (u64)(tcA - tc0)); atomicAdd(p.phase_cycles + 13, (u64)(tcB - tcA)); })
+        PH(if (tid == 0) { if (!LEVC) atomicAdd(p.phase_cycles + 12, (u64)(tcA - tc0)); atomicAdd(p.phase_cycles + 13, (u64)(tcB - tcA)); })
 
         const u64 data_base = tr.static_off + FILE_HDR + 4ull + 20ull * tr.n_frames;   // writer.rs:51, 89-95
 
@@ -1545,6 +1614,8 @@ __global__ void __launch_bounds__(NT, FLO_VARIANT_CTAS) k_encode_frames(const En
         for (u32 c0 = 0; c0 < C; c0 += GROUP) {
             const int nch = (int)min((u32)GROUP, C - c0);
             __syncthreads();
+            for (int i = tid; i < GROUP * NCAND * NWARP; i += NT) { (&s.partA[0][0][0])[i] = 0; (&s.partS[0][0][0])[i] = 0; }
+            for (int i = tid; i < GROUP * NLPC * 2 * NWARP; i += NT) (&s.partT[0][0][0][0])[i] = 0;
             if (tid < nch) {
                 ChanState &cs = s.cs[tid];
                 const u32 c = c0 + tid;
@@ -1575,6 +1646,7 @@ __global__ void __launch_bounds__(NT, FLO_VARIANT_CTAS) k_encode_frames(const En
             __syncthreads();
             PH(const long long ta1 = clock64();)
             if ((tid >> 5) < nch && s.cs[tid >> 5].n > 0) after_pass1_warp<P>(s.cs[tid >> 5], fmax, lpc_on);
+            LV(if (tid == 0) atomicAdd(p.phase_cycles + 14, (u64)(clock64() - ta1)); if (tid == 32) atomicAdd(p.phase_cycles + 12, (u64)(clock64() - ta1));)
             __syncthreads();
             PH(const long long ta2 = clock64();)
             bool run2 = false;
@@ -1636,7 +1708,26 @@ __global__ void __launch_bounds__(NT, FLO_VARIANT_CTAS) k_encode_frames(const En
                     r.nbytes = (u32)best;
                     for (int j = 0; j < MAXORD; j++) r.coef[j] = (r.kind == 2 && j < r.order) ? cs.qc[r.order - 5][j] : 0;
                     r.shift = r.kind == 2 ? cs.lpc_shift[r.order - 5] : 0;
+                    // payload bits of every packer region (rice.rs:97-113 summed over the region's samples)
+                    const int W = nch == 2 ? NWARP / 2 : NWARP;
+                    u64 allbits = 0;
+                    for (int w = 0; w < 16; w++) {
+                        u64 b = 0;
+                        if (w < W) {
+                            const u64 cnt = region_samples(cs.n, W, w);
+                            if (bj == 0) b = 16ull * cnt;
+                            else {
+                                const int src = cs.cand_src[bj];
+                                const u64 S = src == 0 ? s.partS[tid][bj][w] : s.partT[tid][bj - 6][src - 1][w];
+                                b = r.k >= 1 ? S + cnt * (u64)(1 + r.k) : S + s.partA[tid][bj][w] + cnt;
+                            }
+                        }
+                        r.regbits[w] = b;
+                        allbits += b;
+                    }
+                    if (((allbits + 7) >> 3) != (u64)r.nbytes) atomicExch(p.err, 0xBAD00004u);
                 }
+                if (cs.n == 0) for (int w = 0; w < 16; w++) r.regbits[w] = 0;
                 r.pad[0] = r.pad[1] = r.pad[2] = 0;
                 cres[c] = r;
                 if (p.report && c < REPORT_CH) {
@@ -1682,12 +1773,26 @@ __global__ void __launch_bounds__(NT, FLO_VARIANT_CTAS) k_encode_frames(const En
             o[fpos + 5] = (uint8_t)(ms ? 1 : 0);
         }
         u64 pos = fpos + 6;
-        for (u32 c = 0; c < C; c++) {
-            const ChanResult r = cres[c];
-            const u32 hdr = chan_hdr_bytes(all_raw, r);
+        const int wid = tid >> 5;
+        for (u32 c0 = 0; c0 < C; c0 += GROUP) {
+            // the channels of a group are packed side by side (even warps: first channel, odd warps: second one),
+            // every warp its own region of the channel -- the same regions the analysis passes summed over
+            const int nchp = (int)min((u32)GROUP, C - c0);
+            const int cq = nchp == 2 ? (wid & 1) : 0;
+            const int wi = nchp == 2 ? (wid >> 1) : wid;
+            const int W = nchp == 2 ? NWARP / 2 : NWARP;
+            u64 cpos[GROUP];
+            u32 chdr[GROUP];
+            for (int q = 0; q < nchp; q++) {
+                const ChanResult &r = cres[c0 + q];
+                chdr[q] = chan_hdr_bytes(all_raw, r);
+                cpos[q] = pos;
+                pos += 4 + chdr[q] + r.nbytes;
+            }
             __syncthreads();
-            if (tid == 0) {
-                ChanState &cs = s.cs[0];
+            if (tid < nchp) {
+                ChanState &cs = s.cs[tid];
+                const u32 c = c0 + tid;
                 u32 cl = len > c ? (len - c + C - 1) / C : 0;
                 if (ms) cl = len >> 1;
                 cs.n = (int)cl;
@@ -1698,12 +1803,18 @@ __global__ void __launch_bounds__(NT, FLO_VARIANT_CTAS) k_encode_frames(const En
                 cs.pb = planes + stride;
                 cs.glob = planes != smem_planes;
             }
-            if (tid < MAXORD) { s.wcoef[tid] = r.coef[tid]; s.wqd[tid] = ldexp((double)r.coef[tid], -r.shift); }
+            if (tid < nchp * MAXORD) {
+                const ChanResult &r = cres[c0 + tid / MAXORD];
+                s.wqd[tid / MAXORD][tid % MAXORD] = ldexp((double)r.coef[tid % MAXORD], -r.shift);
+            }
+            for (int i = tid; i < GROUP * (NWARP + 1); i += NT) (&s.edge[0][0])[i] = 0;
             __syncthreads();
-            if (tid == 0) {
-                put_u32le(o + pos, hdr + r.nbytes);
+            const ChanResult &r = cres[c0 + cq];
+            if (wi == 0 && (tid & 31) == 0) {
+                const u64 cp = cpos[cq];
+                put_u32le(o + cp, chdr[cq] + r.nbytes);
                 if (!all_raw) {
-                    uint8_t *h = o + pos + 4;
+                    uint8_t *h = o + cp + 4;
                     const u32 nco = r.kind == 2 ? (u32)r.order : 0u;
                     *h++ = (uint8_t)nco;
                     for (u32 j = 0; j < nco; j++) { put_u32le(h, (u32)r.coef[j]); h += 4; }
@@ -1712,8 +1823,30 @@ __global__ void __launch_bounds__(NT, FLO_VARIANT_CTAS) k_encode_frames(const En
                     if (r.kind != 0) *h++ = (uint8_t)r.k;
                 }
             }
-            if (r.kind != 3 && r.nbytes > 0) pack_channel<P>(s, ring, s.cs[0], r, o, pos + 4 + hdr, p.err, p.phase_cycles);
-            pos += 4 + hdr + r.nbytes;
+            const u64 pay = cpos[cq] + 4 + chdr[cq];
+            if (r.kind != 3 && r.nbytes > 0) pack_region<P>(s, ring + wid * WRING, s.cs[cq], cq, r, o, pay, wi, W, p.err);
+            __syncthreads();
+            // words shared by two regions: one lane per channel merges what the regions left in the edge accumulators
+            if (wi == 0 && (tid & 31) == 0 && r.kind != 3 && r.nbytes > 0) {
+                const u64 abase = pay & ~15ull, lo = pay, hi = pay + r.nbytes;
+                u64 bp = (pay & 15ull) * 8ull;
+                u32 curw = 0xffffffffu, curv = 0;
+                auto flushw = [&]() {
+                    if (curw != 0xffffffffu) {
+                        const u64 a = abase + 4ull * curw;
+                        for (int b = 0; b < 4; b++)
+                            if (a + b >= lo && a + b < hi) o[a + b] = (uint8_t)(curv >> (24 - 8 * b));
+                    }
+                };
+                for (int bd = 1; bd < W; bd++) {
+                    bp += r.regbits[bd - 1];
+                    if ((bp & 31) == 0) continue;
+                    const u32 w = (u32)(bp >> 5);
+                    if (w != curw) { flushw(); curw = w; curv = 0; }
+                    curv |= s.edge[cq][bd];
+                }
+                flushw();
+            }
         }
         if (tid == 0 && pos - fpos != fsize) atomicExch(p.err, 0xBAD00002u);
         PH(if (tid == 0) {

@@ -412,10 +412,10 @@ static int encode_batch_impl(flo_ctx *c, const flo_track *tracks, size_t n_track
     const size_t plane_bytes = L.max_plane_elems * 2;
     // Shared memory of a CTA: its fixed state, a work area (ingest stages of the bulk async copies, then the
     // packer's 16 KB staging ring) and, when they fit, the sample planes.  A stage is one step of all threads.
-    const size_t WORK_MIN = (size_t)RING_WORDS * 4;
+    auto work_min = [&](const EncodeVariant &v) { return (size_t)v.threads * 64; };   // one 2 KB ring per warp
     auto share_of = [&](const EncodeVariant &v) { return v.ctas_per_sm > 1 ? c->smem_optin / v.ctas_per_sm - 1024 : c->smem_optin; };
     auto stage_of = [&](const EncodeVariant &v) { return (size_t)v.threads * (v.threads >= 512 ? 4 : 8) * (size_t)std::max<uint64_t>(L.max_group_bytes, 2); };
-    auto fits = [&](const EncodeVariant &v) { return v.static_smem() + plane_bytes + std::max(WORK_MIN, 2 * stage_of(v)) <= share_of(v); };
+    auto fits = [&](const EncodeVariant &v) { return v.static_smem() + plane_bytes + std::max(work_min(v), 2 * stage_of(v)) <= share_of(v); };
     const EncodeVariant *var = &encode_variant(512);
     if (fits(encode_variant(128))) var = &encode_variant(128);
     else if (fits(encode_variant(256))) var = &encode_variant(256);
@@ -424,9 +424,9 @@ static int encode_batch_impl(flo_ctx *c, const flo_track *tracks, size_t n_track
     if (const char *e = getenv("FLO_B200_VARIANT")) var = &encode_variant(atoi(e));
     const size_t smem_static = var->static_smem();
     const bool planes_in_smem = fits(*var);
-    size_t work = std::max(WORK_MIN, 4 * stage_of(*var));
+    size_t work = std::max(work_min(*var), 4 * stage_of(*var));
     work = std::min(work, (share_of(*var) - smem_static - (planes_in_smem ? plane_bytes : 0)) & ~(size_t)127);
-    if (const char *e = getenv("FLO_B200_WORK_KB")) work = std::max(WORK_MIN, (size_t)atoi(e) * 1024);
+    if (const char *e = getenv("FLO_B200_WORK_KB")) work = std::max(work_min(*var), (size_t)atoi(e) * 1024);
     size_t dyn, plane_cap;
     if (planes_in_smem) { dyn = share_of(*var); plane_cap = dyn - smem_static - work; }
     else { dyn = smem_static + work; plane_cap = 0; }                     // global (L2) planes

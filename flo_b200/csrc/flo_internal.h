@@ -50,6 +50,7 @@ struct ChanResult {
     int32_t coef[MAXORD];
     int32_t shift;                    // LPC shift_bits (lpc.rs:266-268; always 15 in practice)
     int32_t pad[3];
+    unsigned long long regbits[16];   // payload bits of each packer region (one region per warp of the channel)
 };
 
 struct EncodeParams {
