@@ -3,22 +3,28 @@
 
     python bench.py --gpus N --steps K --warmup W            # the CUDA path (this repo)
     python bench.py --impl reference --gpus N --steps K ...  # CPU baseline: the oracle port on host cores
+    python bench.py --config {2,3,4,5}                       # which BASELINE config is the workload
 
-A step = one pass of the whole encode path over one batch of synthetic PCM:
-  N = 1 : BASELINE config 2 -- one 1-hour 44.1 kHz 16-bit stereo multitone+noise stream (3600 frames),
-          given to Encoder::encode as interleaved f32 (the documented entry), level 5.
-  N > 1 : BASELINE config 3 (batch corpus of 3-min tracks) sharded over ranks, weak scaling: every rank
-          encodes 20 x 180 s tracks per step (the same 3600 frames / GPU as N = 1); no collective on the
-          data path, one all_gather of per-rank byte lengths per step for the final concatenation.
-`value` = PCM GB/s (2 bytes x interleaved samples / time) over all ranks with inputs resident in HBM;
-`e2e` = the same through the host-buffer C-ABI call (H2D of the f32 samples and D2H of the .flo bytes
-inside the timed region).  Prints ONE JSON line on rank 0.
+A step = one pass of the whole encode path over one batch of synthetic PCM.  Workloads (BASELINE.json configs):
+  2 (default at N = 1): one 1-hour 44.1 kHz 16-bit stereo multitone+noise stream (3600 frames), level 5.
+  3 (default at N > 1): batch corpus of 3-minute 44.1 kHz stereo tracks sharded over ranks, weak scaling:
+      every rank encodes --tracks (default 20) x 180 s per step; no collective on the data path, one
+      all_gather of per-rank byte lengths per step for the final concatenation.
+  4: hi-res 96 kHz stereo sweep+noise, bit_depth 24 in the header, level 9 (maximum LPC order), 600 s.
+  5: 8 kHz mono speech-like signal, 4096 tracks of 8 s (small frames), level 5.
+Every workload enters through Encoder::encode's documented input (interleaved f32).
+`value` = PCM GB/s (2 bytes x interleaved samples / time; 3 bytes for the nominal 24-bit config 4) over all
+ranks with inputs resident in HBM; `e2e` = the same through the host-buffer C-ABI call (H2D of the f32
+samples and D2H of the .flo bytes inside the timed region).  `parity` compares the timed output, frame by
+frame, with the CPU oracle on the sample the CPU baseline encodes anyway; a mismatch fails the run.
+Prints ONE JSON line on rank 0.
 """
 from __future__ import annotations
 
 import argparse
 import json
 import os
+import struct
 import subprocess
 import sys
 import threading
@@ -28,9 +34,31 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.join(ROOT, "tools"))
 
-SR, CH, LEVEL = 44100, 2, 5
-TRACK_SECONDS = 180
 SEED = 0xF10 + 2
+
+# BASELINE.json configs: (sample_rate, channels, header bit depth, level, signal, noise lsb, nominal PCM bytes / sample)
+CONFIGS = {
+    2: dict(sr=44100, ch=2, bits=16, level=5, kind="multitone", noise=64, pcm_bytes=2,
+            name="1-hour 44.1 kHz 16-bit stereo synthetic multitone+noise, single stream (BASELINE config 2)"),
+    3: dict(sr=44100, ch=2, bits=16, level=5, kind="multitone", noise=64, pcm_bytes=2,
+            name="batch corpus shard of 3-minute 44.1 kHz 16-bit stereo tracks (BASELINE config 3)"),
+    4: dict(sr=96000, ch=2, bits=24, level=9, kind="sweep", noise=32, pcm_bytes=3,
+            name="hi-res 96 kHz 24-bit stereo synthetic sweep+noise at maximum LPC order (BASELINE config 4)"),
+    5: dict(sr=8000, ch=1, bits=16, level=5, kind="speech", noise=16, pcm_bytes=2,
+            name="8 kHz mono telephone-band speech-like signal, many short tracks (BASELINE config 5)"),
+}
+
+
+def track_lengths(cfg_id: int, args, world: int) -> list[int]:
+    """Sample frames per track of the WHOLE job (all ranks)."""
+    c = CONFIGS[cfg_id]
+    if cfg_id == 2:
+        return [args.seconds * c["sr"]] * world
+    if cfg_id == 3:
+        return [180 * c["sr"]] * (args.tracks * world)
+    if cfg_id == 4:
+        return [min(args.seconds, 600) * c["sr"]] * world
+    return [8 * c["sr"]] * (4096 * world)
 
 
 def peaks() -> tuple[float, str]:
@@ -99,25 +127,61 @@ def host_threads() -> int:
         return max(1, os.cpu_count() or 1)
 
 
-def cpu_encode_seconds(pcm_np, seconds: int, threads: int, level: int = LEVEL):
-    """Times the oracle (CPU port of the reference algorithm) on `seconds` one-second slices of the
-    stream, `threads` slices at a time (frames are independent in the reference: encoder.rs:53-61)."""
-    from concurrent.futures import ThreadPoolExecutor
-    import numpy as np
+def oracle_mod():
     sys.path.insert(0, os.path.join(ROOT, "oracle"))
     import flo_oracle as oracle                      # checker / CPU baseline only
     oracle.lib()
-    per = SR * CH
-    # one slice per thread, each a contiguous run of whole frames
-    seconds = max(threads, seconds // threads * threads)
-    run = seconds // threads
-    slices = [np.ascontiguousarray(pcm_np[i * run * per:(i + 1) * run * per]).astype(np.float32) * np.float32(1 / 32768)
-              for i in range(threads)]
+    return oracle
+
+
+def cpu_encode(jobs, sr: int, ch: int, bits: int, level: int, threads: int):
+    """Times the oracle (CPU port of the reference algorithm) on `jobs` (interleaved f32 arrays made of whole
+    frames; frames are independent in the reference: encoder.rs:53-61), `threads` jobs at a time.
+    Returns (seconds of wall clock, the .flo images)."""
+    from concurrent.futures import ThreadPoolExecutor
+    oracle = oracle_mod()
     t0 = time.perf_counter()
     with ThreadPoolExecutor(threads) as ex:
-        outs = list(ex.map(lambda s: len(oracle.encode(s, SR, CH, 16, level, b"")), slices))
-    dt = time.perf_counter() - t0
-    return dt, seconds, sum(outs)
+        outs = list(ex.map(lambda s: oracle.encode(s, sr, ch, bits, level, b""), jobs))
+    return time.perf_counter() - t0, outs
+
+
+def flo_frames(img) -> list[tuple[int, int]]:
+    """(position, size) of every frame of a .flo image, from its TOC (writer.rs:39-100, 193-224)."""
+    mv = memoryview(img)
+    assert bytes(mv[:4]) == b"FLO!", "not a flo image"
+    toc_size = struct.unpack_from("<Q", mv, 38)[0]
+    n = struct.unpack_from("<I", mv, 70)[0]
+    data0 = 70 + toc_size
+    out = []
+    for i in range(n):
+        _idx, off, size, _ts = struct.unpack_from("<IQII", mv, 74 + 20 * i)
+        out.append((data0 + off, size))
+    return out
+
+
+def cpu_jobs_for(cfg_id: int, c: dict, pcm_tracks, threads: int, sample_s: int):
+    """The bounded CPU sample of the workload: a list of (track index, first frame, f32 samples of whole frames)."""
+    import numpy as np
+    sr, ch = c["sr"], c["ch"]
+    per = sr * ch
+    jobs = []
+    if cfg_id in (2, 4):
+        # slices of the first `sample_s` seconds of the stream, one per thread, each a run of whole frames
+        total_s = pcm_tracks[0].numel() // per
+        sample_s = min(sample_s, total_s)
+        run = max(1, sample_s // threads)
+        for i in range(min(threads, max(1, sample_s // run))):
+            seg = pcm_tracks[0][i * run * per:(i + 1) * run * per].cpu().numpy()
+            jobs.append((0, i * run, seg.astype(np.float32) * np.float32(1 / 32768)))
+    else:
+        # whole tracks
+        per_track_s = pcm_tracks[0].numel() // per
+        ntr = max(threads, min(len(pcm_tracks), max(1, sample_s // max(1, per_track_s))))
+        ntr = min(ntr, len(pcm_tracks))
+        for t in range(ntr):
+            jobs.append((t, 0, pcm_tracks[t].cpu().numpy().astype(np.float32) * np.float32(1 / 32768)))
+    return jobs
 
 
 def main() -> int:
@@ -126,28 +190,34 @@ def main() -> int:
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--seconds", type=int, default=3600, help="audio seconds per GPU per step")
-    ap.add_argument("--level", type=int, default=LEVEL)
+    ap.add_argument("--config", type=int, default=0, choices=[0, 2, 3, 4, 5], help="BASELINE config (0 = 2 at N=1, 3 at N>1)")
+    ap.add_argument("--seconds", type=int, default=3600, help="audio seconds per GPU per step (configs 2 and 4)")
+    ap.add_argument("--tracks", type=int, default=20, help="config 3: tracks of 180 s per GPU per step")
+    ap.add_argument("--level", type=int, default=-1, help="override the config's compression level")
     ap.add_argument("--cpu-sample-seconds", type=int, default=0, help="0 = auto (about 15 s of CPU work)")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
-    ap.add_argument("--no-extras", action="store_true", help="skip the per-level / PCM16-entry side measurements")
+    ap.add_argument("--no-extras", action="store_true", help="skip the per-level / other-config side measurements")
     args = ap.parse_args()
-    level = args.level
 
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     n_gpus = max(args.gpus, world)
+    cfg_id = args.config or (2 if world == 1 else 3)
+    c = CONFIGS[cfg_id]
+    SR, CH, BITS = c["sr"], c["ch"], c["bits"]
+    level = c["level"] if args.level < 0 else args.level
     peak, peak_src = peaks()
-    seconds = args.seconds
-    n_inter = seconds * SR * CH
-    workload = (f"1-hour 44.1 kHz 16-bit stereo synthetic multitone+noise, single stream (BASELINE config 2)"
-                if world == 1 else
-                f"batch corpus shard: {seconds // TRACK_SECONDS} x {TRACK_SECONDS} s 44.1 kHz 16-bit stereo tracks per GPU per step (BASELINE config 3)")
-    config = {"workload": workload, "audio_seconds_per_gpu_per_step": seconds, "sample_rate": SR, "channels": CH,
-              "level": level, "entry": "Encoder::encode (interleaved f32)", "frames_per_gpu_per_step": seconds,
-              "l2": "inputs (1.27 GB f32 per step) are 10x the 126 MB L2; no flush needed",
+    corpus_n = track_lengths(cfg_id, args, world)
+    per_gpu_tracks = len(corpus_n) // world
+    per_gpu_seconds = sum(corpus_n[:per_gpu_tracks]) / SR
+    workload = c["name"] + (f": {per_gpu_tracks} x {corpus_n[0] // SR} s per GPU per step" if cfg_id in (3, 5) else "")
+    config = {"workload": workload, "baseline_config": cfg_id, "audio_seconds_per_gpu_per_step": per_gpu_seconds,
+              "tracks_per_gpu_per_step": per_gpu_tracks, "sample_rate": SR, "channels": CH, "bit_depth": BITS,
+              "level": level, "entry": "Encoder::encode (interleaved f32)",
+              "frames_per_gpu_per_step": sum(-(-n // SR) for n in corpus_n[:per_gpu_tracks]),
+              "l2": "inputs (%.2f GB f32 per GPU per step) exceed the 126 MB L2; no flush needed" % (4e-9 * sum(corpus_n[:per_gpu_tracks]) * CH),
               "parallelism": f"{n_gpus} x independent shards, no data-path collective"}
 
     import numpy as np
@@ -159,24 +229,37 @@ def main() -> int:
         sys.path.insert(0, os.path.join(ROOT, "tests"))
         from helpers import synth_pcm16 as np_synth
         threads = host_threads()
-        sample_s = args.cpu_sample_seconds or 60 * threads
-        pcm = np_synth(sample_s * SR, CH, SR, seed=SEED, kind="multitone", noise_lsb=64)
+        sample_s = args.cpu_sample_seconds or (60 * threads if cfg_id != 4 else 12 * threads)
+        per = SR * CH
+        if cfg_id in (2, 4):
+            run = max(1, sample_s // threads)
+            pcm = np_synth(run * threads * SR, CH, SR, seed=SEED, kind=c["kind"], noise_lsb=c["noise"])
+            jobs = [pcm[i * run * per:(i + 1) * run * per].astype(np.float32) * np.float32(1 / 32768) for i in range(threads)]
+        else:
+            tlen = corpus_n[0]
+            ntr = max(threads, sample_s // max(1, tlen // SR))
+            jobs = [np_synth(tlen, CH, SR, seed=SEED + 131 * t, kind=c["kind"], noise_lsb=c["noise"]).astype(np.float32) * np.float32(1 / 32768)
+                    for t in range(ntr)]
+        secs = sum(j.size for j in jobs) / per
         for _ in range(min(args.warmup, 1)):
-            cpu_encode_seconds(pcm, threads, threads, level)
+            cpu_encode(jobs[:threads], SR, CH, BITS, level, threads)
         dts = []
         for _ in range(args.steps):
-            dt, secs, nbytes = cpu_encode_seconds(pcm, sample_s, threads, level)
+            dt, _outs = cpu_encode(jobs, SR, CH, BITS, level, threads)
             dts.append(dt)
         dt = sum(dts) / len(dts)
-        samples = secs * SR * CH
-        val = 2.0 * samples / dt / 1e9
+        samples = secs * per
+        val = c["pcm_bytes"] * samples / dt / 1e9
         line = {"impl": "reference", "metric": "lossless encode PCM throughput", "value": val, "unit": "GB/s",
                 "n_gpus": n_gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt * 1e3,
+                "audio_seconds_per_step": secs,
+                "ms_per_step_scaled_to_workload": dt * 1e3 * per_gpu_seconds / secs,
                 "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "int32/int64 + f64 Levinson",
                 "data": "synthetic", "config": config, "x_realtime": secs / dt,
                 "cpu_baseline": {"value": val, "unit": "GB/s", "cores": threads, "kind": "port",
-                                 "sample": f"{secs} s of the stream as {threads} independent slices, one thread each; "
-                                           "C oracle (literal restatement of the reference encoder, gcc -O2), "
+                                 "sample": f"{secs:.0f} s of the workload as {len(jobs)} independent jobs of whole frames, "
+                                           f"{threads} at a time, one thread each (ms_per_step is the time of this sample); "
+                                           "C oracle (literal restatement of the reference encoder, gcc -O3), "
                                            "the Rust reference cannot be built here (no cargo)"},
                 "e2e": {"value": val, "unit": "GB/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
         print(json.dumps(line))
@@ -192,6 +275,13 @@ def main() -> int:
     dev = torch.device("cuda", local_rank)
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
+        # one block of host cores per rank: the ranks' copy threads and pinned buffers do not share cores
+        try:
+            cores = sorted(os.sched_getaffinity(0))
+            k = max(1, len(cores) // world)
+            os.sched_setaffinity(0, set(cores[local_rank * k:(local_rank + 1) * k]) or set(cores))
+        except Exception:
+            pass
     ctx = flo_b200.Context(local_rank)
     sampler = ClockSampler(local_rank)
     if rank == 0:
@@ -201,25 +291,21 @@ def main() -> int:
 
     # synthetic PCM directly in HBM (integer-only generator, identical to tests/helpers.synth_pcm16)
     from flo_b200 import shard
-    if world == 1:
-        corpus_n = [seconds * SR]
-    else:
-        corpus_n = [TRACK_SECONDS * SR] * (world * (seconds // TRACK_SECONDS))      # the whole job's tracks
     ranges = shard.partition_tracks([shard.frames_of_track(n * CH, SR, CH) for n in corpus_n], world)
     t_lo, t_hi = ranges[rank]                                                       # this rank's contiguous shard
     tracks_n = corpus_n[t_lo:t_hi]
-    pcm_tracks = [synth_torch.synth_pcm16_long(n, CH, SR, SEED + 131 * (t_lo + i), "multitone", 64, dev)
+    pcm_tracks = [synth_torch.synth_pcm16_long(n, CH, SR, SEED + 131 * (t_lo + i), c["kind"], c["noise"], dev)
                   for i, n in enumerate(tracks_n)]
     f32_tracks = [p.to(torch.float32) * (1.0 / 32768.0) for p in pcm_tracks]    # reflo/src/audio.rs:247-254 (exact)
     n_list = [int(t.numel()) for t in f32_tracks]
+    nt = len(n_list)
     total_inter = sum(n_list)
-    bound = ctx.output_bound(n_list, [SR] * len(n_list), [CH] * len(n_list))
+    bound = ctx.output_bound(n_list, [SR] * nt, [CH] * nt)
     d_out = torch.empty(bound, dtype=torch.uint8, device=dev)
     ptrs = [t.data_ptr() for t in f32_tracks]
 
     def step():
-        off, ln = ctx.encode_batch_device(ptrs, n_list, [SR] * len(ptrs), [CH] * len(ptrs), [16] * len(ptrs),
-                                          d_out.data_ptr(), bound, level=level)
+        off, ln = ctx.encode_batch_device(ptrs, n_list, [SR] * nt, [CH] * nt, [BITS] * nt, d_out.data_ptr(), bound, level=level)
         if world > 1:       # per-track byte lengths for the final concatenation (the only exchange), non-blocking
             pending.append(shard.exchange_lengths_async([int(v) for v in ln], ranges))
         return off, ln
@@ -242,7 +328,7 @@ def main() -> int:
     enc_ms, dev_ms, launches = [], [], 0
     ev0.record()
     for _ in range(args.steps):
-        step()
+        off, ln = step()
         t = ctx.last_timing()
         enc_ms.append(t["encode_ms"]); dev_ms.append(t["device_ms"]); launches += t["launches"]
     ev1.record()
@@ -254,7 +340,7 @@ def main() -> int:
     if world > 1:
         dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
     ms_step = float(tmax.item()) / args.steps
-    value = 2.0 * total_inter * world / (ms_step * 1e-3) / 1e9
+    value = c["pcm_bytes"] * total_inter * world / (ms_step * 1e-3) / 1e9
 
     # roofline of the dominant kernel (k_encode_frames): algorithmic bytes = f32 in + .flo out
     k_ms = sum(enc_ms) / len(enc_ms)
@@ -262,22 +348,58 @@ def main() -> int:
     achieved = alg_bytes / (k_ms * 1e-3) / 1e9
     traffic = None                      # DRAM bytes per launch from the committed ncu capture of this exact workload
     try:
-        with open(os.path.join(ROOT, "profiles", "r01_traffic.json")) as f:
+        with open(os.path.join(ROOT, "profiles", "r02_traffic.json")) as f:
             tj = json.load(f)
-        if world == 1 and tj["frames"] == seconds and tj["level"] == level:
+        if world == 1 and cfg_id == 2 and tj["frames"] == args.seconds and tj["level"] == level:
             traffic = tj["dram_bytes_read"] + tj["dram_bytes_write"]
     except Exception:
         pass
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                 "traffic": traffic, "kernel": "k_encode_frames", "kernel_ms": k_ms, "peak_source": peak_src,
                 "algorithmic_bytes_per_launch": alg_bytes,
-                "note": "issue/ALU-pipe bound at level 5 (10 exhaustive candidates per channel: ~200 thread-instructions per "
-                        "channel-sample); DRAM traffic is 1.07 x the algorithmic bytes (some write-back of the L2-resident "
-                        "16-bit planes, no re-reads of the input); see DESIGN.md section 6"}
+                "note": "latency / issue bound, not bandwidth bound (exhaustive candidate search of the reference: "
+                        "~190 thread-instructions per channel-sample at level 5, FP64-pipe FIR); DRAM traffic stays "
+                        "near the algorithmic bytes (input read once, 16-bit planes live in L2); see DESIGN.md section 6"}
 
-    # side measurements (not the headline): other compression levels and the PCM16 entry, same stream
+    # ---- byte parity of the timed output against the CPU oracle + CPU baseline on the same sample ----
+    cpu = None
+    parity = None
+    if rank == 0 and not args.no_cpu:
+        threads = host_threads()
+        sample_s = args.cpu_sample_seconds or (60 * threads if cfg_id != 4 else 12 * threads)
+        jobs = cpu_jobs_for(cfg_id, c, pcm_tracks, threads, sample_s)
+        dt, outs = cpu_encode([j[2] for j in jobs], SR, CH, BITS, level, threads)
+        secs = sum(j[2].size for j in jobs) / (SR * CH)
+        host_img = d_out.cpu().numpy()
+        gpu_frames = {}
+        checked, same = 0, True
+        first_bad = None
+        for (t, f0, _x), ref in zip(jobs, outs):
+            if t not in gpu_frames:
+                gpu_frames[t] = (int(off[t]), flo_frames(host_img[int(off[t]):int(off[t]) + int(ln[t])]))
+            base, gfr = gpu_frames[t]
+            for i, (rp, rs) in enumerate(flo_frames(ref)):
+                gp, gs = gfr[f0 + i]
+                ok = gs == rs and bytes(host_img[base + gp:base + gp + gs]) == ref[rp:rp + rs]
+                checked += 1
+                if not ok and same:
+                    same, first_bad = False, {"track": t, "frame": f0 + i}
+        parity = {"checker": "CPU oracle (C restatement of the reference encoder)", "frames_checked": checked,
+                  "audio_seconds_checked": secs, "identical": same, "first_mismatch": first_bad}
+        # single-thread figure: what one Encoder::encode call is in the reference
+        x1 = jobs[0][2][:min(jobs[0][2].size, 20 * SR * CH)]
+        dt1, _ = cpu_encode([x1], SR, CH, BITS, level, 1)
+        cpu = {"value": c["pcm_bytes"] * secs * SR * CH / dt / 1e9, "unit": "GB/s", "cores": threads, "kind": "port",
+               "sample": f"{secs:.0f} s of the same input as {len(jobs)} jobs of whole frames, {threads} at a time, one thread each "
+                         "(C oracle, gcc -O3)",
+               "x_realtime": secs / dt,
+               "single_thread": {"value": c["pcm_bytes"] * x1.size / dt1 / 1e9, "unit": "GB/s", "x_realtime": x1.size / (SR * CH) / dt1,
+                                 "sample": f"{x1.size // (SR * CH)} s, one thread (one Encoder::encode call of the reference is single-threaded)"}}
+        del host_img
+
+    # side measurements (not the headline): other compression levels, the PCM16 entry, the other BASELINE configs
     extras = None
-    if world == 1 and not args.no_extras:
+    if world == 1 and cfg_id == 2 and not args.no_extras:
         extras = {"note": "encode-kernel ms per step and % of measured HBM peak on the same 1-hour stream; "
                           "levels 0-3 try fixed predictors only (encoder.rs:204)", "levels": {}}
         for lv in (0, 2, 4, 5, 7, 9):
@@ -306,10 +428,34 @@ def main() -> int:
         k_dec = min(t["encode_ms"] for t in ts)
         extras["decode"] = {"kernel": "k_dec_units", "kernel_ms": k_dec, "device_pass_ms": min(t["device_ms"] for t in ts),
                             "launches": ts[-1]["launches"], "round_trip_exact": bool(n_dec == total_inter and torch.equal(d_dec, q)),
-                            "pct_of_hbm_peak": 100.0 * (4.0 * total_inter + float(l2[0])) / (k_dec * 1e-3) / 1e9 / peak,
-                            "note": "flo_decode_device on the level-5 file of the same stream; latency-bound (one lane per "
-                                    "channel of a frame, reader warp + predictor warp), see DESIGN.md section 9.2"}
+                            "pct_of_hbm_peak": 100.0 * (4.0 * total_inter + float(l2[0])) / (k_dec * 1e-3) / 1e9 / peak}
         del d_dec, q
+
+        # the other BASELINE configs, device-resident (their own bench lines: bench.py --config 3|4|5)
+        extras["configs"] = {}
+        for cid, kw in ((3, dict(tracks=20)), (4, dict(seconds=600)), (5, dict())):
+            cc = CONFIGS[cid]
+
+            lens = track_lengths(cid, argparse.Namespace(seconds=kw.get("seconds", 3600), tracks=kw.get("tracks", 20)), 1)
+            pcs = [synth_torch.synth_pcm16_long(n, cc["ch"], cc["sr"], SEED + 131 * i, cc["kind"], cc["noise"], dev) for i, n in enumerate(lens)]
+            xs = [p.to(torch.float32) * (1.0 / 32768.0) for p in pcs]
+            nn = [int(t.numel()) for t in xs]
+            bb = ctx.output_bound(nn, [cc["sr"]] * len(nn), [cc["ch"]] * len(nn))
+            oo = torch.empty(bb, dtype=torch.uint8, device=dev)
+            best = None
+            for _ in range(4):
+                _o, l3 = ctx.encode_batch_device([t.data_ptr() for t in xs], nn, [cc["sr"]] * len(nn), [cc["ch"]] * len(nn),
+                                                 [cc["bits"]] * len(nn), oo.data_ptr(), bb, level=cc["level"])
+                tt = ctx.last_timing()
+                best = tt if best is None or tt["device_ms"] < best["device_ms"] else best
+            tot = sum(nn)
+            extras["configs"][str(cid)] = {
+                "workload": cc["name"], "tracks": len(nn), "audio_seconds": sum(lens) / cc["sr"], "level": cc["level"],
+                "device_ms": best["device_ms"], "encode_kernel_ms": best["encode_ms"],
+                "value_GBps": cc["pcm_bytes"] * tot / best["device_ms"] / 1e6, "x_realtime": sum(lens) / cc["sr"] / best["device_ms"] * 1e3,
+                "pct_of_hbm_peak_encode_kernel": 100.0 * (4.0 * tot + float(l3.sum())) / best["encode_ms"] / 1e6 / peak,
+                "compression_ratio": 2.0 * tot / float(l3.sum())}
+            del pcs, xs, oo
 
     # e2e: host buffers through the reference-facing C-ABI call (H2D + D2H inside the timed region)
     e2e = None
@@ -318,7 +464,7 @@ def main() -> int:
         for h, d in zip(host_in, f32_tracks):
             h.copy_(d)
         torch.cuda.synchronize()
-        specs = [flo_b200.TrackSpec(h.numpy(), SR, CH, 16, b"") for h in host_in]
+        specs = [flo_b200.TrackSpec(h.numpy(), SR, CH, BITS, b"") for h in host_in]
         for _ in range(2):                                         # warm-up (arena growth, pinned output pool)
             with ctx.encode_batch(specs, level, views=True) as res:
                 e2e_out = res.total_bytes()
@@ -334,9 +480,58 @@ def main() -> int:
         tm = torch.tensor([dt], dtype=torch.float64, device=dev)
         if world > 1:
             dist.all_reduce(tm, op=dist.ReduceOp.MAX)
-        e2e = {"value": 2.0 * total_inter * world / float(tm.item()) / 1e9, "unit": "GB/s",
+        e2e_s = float(tm.item())
+
+        # what the copies alone cost on this box with all ranks copying at once: the same bytes host -> device and
+        # device -> host as plain cudaMemcpyAsync on two streams (no kernel) -- the ceiling e2e can reach
+        h_out = torch.empty(e2e_out, dtype=torch.uint8, pin_memory=True)
+        d_in = torch.empty(total_inter, dtype=torch.float32, device=dev)
+        s_in, s_out = torch.cuda.Stream(), torch.cuda.Stream()
+        big = torch.cat([h.view(-1) for h in host_in]) if len(host_in) > 1 else host_in[0]
+        big = big.pin_memory() if not big.is_pinned() else big
+
+        def copies():
+            with torch.cuda.stream(s_in):
+                d_in.copy_(big, non_blocking=True)
+            with torch.cuda.stream(s_out):
+                h_out.copy_(d_out[:e2e_out], non_blocking=True)
+            s_in.synchronize(); s_out.synchronize()
+        copies()
+        sync_all()
+        t0 = time.perf_counter()
+        for _ in range(reps):
+            copies()
+        dtc = (time.perf_counter() - t0) / reps
+        tc = torch.tensor([dtc], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(tc, op=dist.ReduceOp.MAX)
+        ceil_s = float(tc.item())
+        del h_out, d_in, big
+
+        e2e = {"value": c["pcm_bytes"] * total_inter * world / e2e_s / 1e9, "unit": "GB/s",
                "h2d_bytes_per_step": 4 * total_inter, "d2h_bytes_per_step": e2e_out,
-               "ms_per_step": float(tm.item()) * 1e3, "x_realtime": seconds * world / float(tm.item())}
+               "ms_per_step": e2e_s * 1e3, "x_realtime": per_gpu_seconds * world / e2e_s,
+               "pcie_ceiling_gbs": c["pcm_bytes"] * total_inter * world / ceil_s / 1e9,
+               "pcie_ceiling_ms_per_step": ceil_s * 1e3, "frac_of_pcie_ceiling": ceil_s / e2e_s,
+               "pcie_ceiling_note": "the same H2D and D2H bytes as plain cudaMemcpyAsync from / to pinned memory on two "
+                                    "streams, all ranks at once, no kernel"}
+
+        # the same call from pageable memory (what a Rust &[f32] is): staged through the library's pinned ring
+        if world == 1:
+            pag = [np.array(h.numpy(), copy=True) for h in host_in]
+            specs_p = [flo_b200.TrackSpec(a, SR, CH, BITS, b"") for a in pag]
+            for _ in range(2):
+                with ctx.encode_batch(specs_p, level, views=True) as res:
+                    same_p = res.total_bytes() == e2e_out
+            t0 = time.perf_counter()
+            for _ in range(reps):
+                with ctx.encode_batch(specs_p, level, views=True) as res:
+                    pass
+            dtp = (time.perf_counter() - t0) / reps
+            e2e["pageable_input"] = {"value": c["pcm_bytes"] * total_inter / dtp / 1e9, "unit": "GB/s", "ms_per_step": dtp * 1e3,
+                                     "same_bytes": bool(same_p), "slowdown_vs_pinned": dtp / e2e_s}
+            del pag, specs_p
+
         if extras is not None and world == 1:
             # same call with reflo's 16-bit PCM as the host buffer (flo_encode_pcm16): half the H2D bytes
             host_pcm = [torch.empty(n, dtype=torch.int16, pin_memory=True) for n in n_list]
@@ -357,30 +552,24 @@ def main() -> int:
             del host_pcm, specs16
         del host_in, specs
 
-    cpu = None
-    if rank == 0 and world == 1 and not args.no_cpu:
-        threads = host_threads()
-        sample_s = args.cpu_sample_seconds or 60 * threads
-        pcm_np = pcm_tracks[0][:sample_s * SR * CH].cpu().numpy()
-        dt, secs, _ = cpu_encode_seconds(pcm_np, sample_s, threads, level)
-        cpu = {"value": 2.0 * secs * SR * CH / dt / 1e9, "unit": "GB/s", "cores": threads, "kind": "port",
-               "sample": f"first {secs} s of the same stream as {threads} slices, one thread each (C oracle, gcc -O2)",
-               "x_realtime": secs / dt}
-
+    rc = 0
     if rank == 0:
         line = {"metric": "lossless encode PCM throughput", "value": value, "unit": "GB/s", "n_gpus": n_gpus,
                 "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms_step, "higher_is_better": True,
                 "scaling": "weak", "vs_baseline": None, "dtype": "int32/int64 + f64 Levinson", "data": "synthetic",
-                "config": config, "x_realtime": seconds * world / (ms_step * 1e-3),
+                "config": config, "x_realtime": per_gpu_seconds * world / (ms_step * 1e-3),
                 "pct_of_hbm_peak": 100.0 * achieved / peak, "flo_bytes_per_step_per_gpu": out_bytes,
                 "compression_ratio": 2.0 * total_inter / out_bytes, "roofline": roofline, "cpu_baseline": cpu,
-                "e2e": e2e, "gpu_launches": launches, "clocks": clocks,
+                "parity": parity, "e2e": e2e, "gpu_launches": launches, "clocks": clocks,
                 "device_ms_per_step": sum(dev_ms) / len(dev_ms), "analysis_counters_last_step": counters,
                 "extras": extras}
         print(json.dumps(line))
+        if parity is not None and not parity["identical"]:
+            print("bench.py: the timed output differs from the CPU oracle: " + json.dumps(parity), file=sys.stderr)
+            rc = 3
     if world > 1:
         dist.destroy_process_group()
-    return 0
+    return rc
 
 
 if __name__ == "__main__":

@@ -620,13 +620,10 @@ struct Sweeps {
     static constexpr int NO = HI - LO + 1;
     static __device__ __forceinline__ void run(const ChanState &cs, const i32 (&x)[NH + CH], LpcStat *st /* by order - LO0 */, int lo0) {
         if constexpr (LO <= HI) {
-#ifdef FLO_SINGLE_SWEEPS
-            constexpr int OA = HI, OB = 0;
-            constexpr int BS = 4;
-#else
-            constexpr int OA = HI, OB = LO < HI ? LO : 0;
-            constexpr int BS = FLO_PAIR_BS;
-#endif
+            // two orders per sweep while their taps fit the register file (13 coefficients), else one
+            constexpr bool PAIR = LO < HI && HI + LO <= 13;
+            constexpr int OA = HI, OB = PAIR ? LO : 0;
+            constexpr int BS = PAIR ? FLO_PAIR_BS : 4;
             const bool oka = cs.lpc_ok[OA - 5] != 0, okb = OB > 0 && cs.lpc_ok[(OB > 0 ? OB : 5) - 5] != 0;
             if (oka || okb) {
                 LpcStat a = st[OA - lo0], b = st[(OB > 0 ? OB : OA) - lo0];
@@ -651,11 +648,7 @@ struct Sweeps {
                 st[OA - lo0] = a;
                 if constexpr (OB > 0) st[OB - lo0] = b;
             }
-#ifdef FLO_SINGLE_SWEEPS
-            Sweeps<NH, LO, HI - 1>::run(cs, x, st, lo0);
-#else
-            Sweeps<NH, LO + 1, HI - 1>::run(cs, x, st, lo0);
-#endif
+            Sweeps<NH, PAIR ? LO + 1 : LO, HI - 1>::run(cs, x, st, lo0);
         }
     }
 };

@@ -10,8 +10,12 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <condition_variable>
 #include <mutex>
+#include <thread>
 #include <vector>
+
+#include <sched.h>
 
 #include "flo_internal.h"
 
@@ -88,7 +92,75 @@ struct HostBuf {                      // grow-only pinned host arena
 };
 
 inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+
+// The library switches to the context's device for the duration of a call and puts the caller's current
+// device back afterwards (a process that also runs other CUDA code keeps its own current device).
+struct DeviceGuard {
+    int prev = -1;
+    cudaError_t err = cudaSuccess;
+    explicit DeviceGuard(int dev) {
+        if (cudaGetDevice(&prev) != cudaSuccess) { cudaGetLastError(); prev = -1; }
+        if (prev != dev) err = cudaSetDevice(dev);
+        else prev = -1;
+    }
+    ~DeviceGuard() { if (prev >= 0) cudaSetDevice(prev); }
+};
 constexpr int MAX_WAVES = 16;
+
+// Host threads that copy pageable caller memory into the pinned staging ring, a slice each (a single thread
+// copies at ~10 GB/s, a fifth of what the PCIe link takes).
+class CopyPool {
+  public:
+    explicit CopyPool(int workers) : n_(workers) {
+        for (int i = 0; i < n_; i++) th_.emplace_back([this, i] { worker(i); });
+    }
+    ~CopyPool() {
+        { std::lock_guard<std::mutex> lk(m_); stop_ = true; gen_++; }
+        cv_.notify_all();
+        for (auto &t : th_) t.join();
+    }
+    // dst[0, bytes) = src[0, bytes), split over the workers and the calling thread
+    void copy(uint8_t *dst, const uint8_t *src, size_t bytes) {
+        const size_t parts = (size_t)n_ + 1;
+        const size_t piece = align_up((bytes + parts - 1) / parts, 4096);
+        if (n_ == 0 || bytes < (1u << 20)) { memcpy(dst, src, bytes); return; }
+        { std::lock_guard<std::mutex> lk(m_); dst_ = dst; src_ = src; bytes_ = bytes; piece_ = piece; pending_ = n_; gen_++; }
+        cv_.notify_all();
+        slice(n_);
+        std::unique_lock<std::mutex> lk(m_);
+        done_.wait(lk, [this] { return pending_ == 0; });
+    }
+  private:
+    static size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+    void slice(int i) {
+        const size_t lo = std::min(bytes_, piece_ * (size_t)i), hi = std::min(bytes_, piece_ * (size_t)(i + 1));
+        if (hi > lo) memcpy(dst_ + lo, src_ + lo, hi - lo);
+    }
+    void worker(int i) {
+        unsigned long long seen = 0;
+        for (;;) {
+            { std::unique_lock<std::mutex> lk(m_); cv_.wait(lk, [&] { return gen_ != seen; }); seen = gen_; if (stop_) return; }
+            slice(i);
+            { std::lock_guard<std::mutex> lk(m_); if (--pending_ == 0) done_.notify_one(); }
+        }
+    }
+    int n_;
+    std::vector<std::thread> th_;
+    std::mutex m_;
+    std::condition_variable cv_, done_;
+    uint8_t *dst_ = nullptr; const uint8_t *src_ = nullptr; size_t bytes_ = 0, piece_ = 0;
+    int pending_ = 0; unsigned long long gen_ = 0; bool stop_ = false;
+};
+constexpr int STAGE_SLOTS = 4;
+constexpr size_t STAGE_SLOT_BYTES = 8u << 20;
+
+inline int copy_workers() {
+    cpu_set_t set;
+    int cores = 1;
+    if (sched_getaffinity(0, sizeof set, &set) == 0) cores = CPU_COUNT(&set);
+    if (const char *e = getenv("FLO_B200_COPY_THREADS")) return std::max(0, atoi(e) - 1);
+    return std::max(0, std::min(7, cores - 1));
+}
 
 // Pinned output blocks.  Large results are copied device -> host straight into one page-locked block
 // and handed out as pointers into it (no second host copy); flo_free() on the last pointer of a
@@ -170,8 +242,14 @@ struct flo_ctx {
     DevBuf conv;                                           // f32 samples of the U8 / S32 ingest pre-pass
     uint64_t counters[24] = {0};      // [0..7] analysis counters, [8..23] per-phase SM clock sums
     HostBuf h_small, h_out;
+    HostBuf stage;                                         // pinned ring for pageable caller buffers
+    cudaEvent_t ev_slot[STAGE_SLOTS] = {};
+    bool slot_used[STAGE_SLOTS] = {};
+    unsigned stage_next = 0;
+    CopyPool *pool = nullptr;
     bool report_on = false;
     size_t persist_max = 0, window_max = 0;          // L2 persisting carve-out limits of the device
+    size_t persist_prev = (size_t)-1;                // the device's persisting-L2 limit before this context raised it
     void *l2_win_ptr = nullptr; size_t l2_win_bytes = 0; cudaStream_t l2_win_stream = nullptr;
     uint32_t report_frames = 0;
     float ms[6] = {0, 0, 0, 0, 0, 0};
@@ -189,7 +267,8 @@ extern "C" int flo_ctx_create(int device, flo_ctx **out) {
         return FLO_ERR_CUDA;
     }
     if (device < 0 || device >= n) { set_err("device %d out of range (0..%d)", device, n - 1); return FLO_ERR_ARG; }
-    CK(cudaSetDevice(device));
+    DeviceGuard dg(device);
+    CK(dg.err);
     cudaDeviceProp prop;
     CK(cudaGetDeviceProperties(&prop, device));
     if (prop.major < 10) { set_err("device %d is sm_%d%d; this library is built for sm_100a only", device, prop.major, prop.minor); return FLO_ERR_CUDA; }
@@ -200,8 +279,16 @@ extern "C" int flo_ctx_create(int device, flo_ctx **out) {
     c->smem_optin = prop.sharedMemPerBlockOptin;
     c->persist_max = (size_t)std::max(0, prop.persistingL2CacheMaxSize);
     c->window_max = (size_t)std::max(0, prop.accessPolicyMaxWindowSize);
-    if (c->persist_max) { cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, c->persist_max); cudaGetLastError(); }
-    cudaError_t e2 = cudaStreamCreateWithFlags(&c->own_stream, cudaStreamNonBlocking);
+    if (c->persist_max) {
+        size_t prev = 0;
+        if (cudaDeviceGetLimit(&prev, cudaLimitPersistingL2CacheSize) == cudaSuccess) c->persist_prev = prev;
+        cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, c->persist_max);
+        cudaGetLastError();
+    }
+    // The context's own stream is a BLOCKING stream: it orders itself against the legacy default stream, so
+    // device inputs produced there (e.g. by torch's default stream) are complete before the kernels read them.
+    // Inputs produced on any other stream: pass that stream with flo_ctx_set_stream (see flo_b200.h).
+    cudaError_t e2 = cudaStreamCreateWithFlags(&c->own_stream, cudaStreamDefault);
     if (e2 != cudaSuccess) { set_err("cudaStreamCreate: %s", cudaGetErrorString(e2)); delete c; return FLO_ERR_CUDA; }
     c->stream = c->own_stream;
     for (auto &ev : c->ev) cudaEventCreate(&ev);
@@ -209,6 +296,7 @@ extern "C" int flo_ctx_create(int device, flo_ctx **out) {
     cudaStreamCreateWithFlags(&c->s_out, cudaStreamNonBlocking);
     for (auto &ev : c->ev_in) cudaEventCreateWithFlags(&ev, cudaEventDisableTiming);
     for (auto &ev : c->ev_k) cudaEventCreateWithFlags(&ev, cudaEventDisableTiming);
+    for (auto &ev : c->ev_slot) cudaEventCreateWithFlags(&ev, cudaEventDisableTiming);
     cudaEventCreateWithFlags(&c->ev_fin, cudaEventDisableTiming);
     upload_crc_tables();
     for (int th : {512, 256, 128}) {
@@ -223,14 +311,25 @@ extern "C" int flo_ctx_create(int device, flo_ctx **out) {
 
 extern "C" void flo_ctx_destroy(flo_ctx *c) {
     if (!c) return;
-    cudaSetDevice(c->device);
+    DeviceGuard dg(c->device);
     cudaDeviceSynchronize();
-    if (c->l2_win_ptr) { cudaCtxResetPersistingL2Cache(); cudaGetLastError(); }
+    if (c->l2_win_ptr) {
+        // take the persisting window off the stream it was installed on and give the L2 set-aside back
+        cudaStreamAttrValue av;
+        memset(&av, 0, sizeof av);
+        if (c->l2_win_stream == c->own_stream || c->l2_win_stream == c->stream) cudaStreamSetAttribute(c->l2_win_stream, cudaStreamAttributeAccessPolicyWindow, &av);
+        cudaCtxResetPersistingL2Cache();
+        cudaGetLastError();
+    }
+    if (c->persist_prev != (size_t)-1) { cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, c->persist_prev); cudaGetLastError(); }
     for (DevBuf *b : {&c->in, &c->out, &c->meta, &c->tracks, &c->frames, &c->ctrl, &c->fexcl, &c->fsize,
                       &c->foff, &c->plane, &c->cres, &c->report, &c->dec_frames, &c->dec_units, &c->dec_base, &c->dec_ctl, &c->conv})
         b->release();
     c->h_small.release();
     c->h_out.release();
+    c->stage.release();
+    delete c->pool;
+    for (auto &ev : c->ev_slot) if (ev) cudaEventDestroy(ev);
     for (auto &ev : c->ev) if (ev) cudaEventDestroy(ev);
     for (auto &ev : c->ev_in) if (ev) cudaEventDestroy(ev);
     for (auto &ev : c->ev_k) if (ev) cudaEventDestroy(ev);
@@ -244,7 +343,17 @@ extern "C" void flo_ctx_destroy(flo_ctx *c) {
 extern "C" int flo_ctx_set_stream(flo_ctx *c, void *cuda_stream) {
     if (!c) { set_err("ctx is NULL"); return FLO_ERR_ARG; }
     std::lock_guard<std::mutex> lk(c->mu);
-    c->stream = cuda_stream ? (cudaStream_t)cuda_stream : c->own_stream;
+    cudaStream_t ns = cuda_stream ? (cudaStream_t)cuda_stream : c->own_stream;
+    if (ns != c->stream && c->l2_win_ptr && c->l2_win_stream == c->stream) {
+        // the persisting access window installed on the stream we leave must not outlive our use of it
+        DeviceGuard dg(c->device);
+        cudaStreamAttrValue av;
+        memset(&av, 0, sizeof av);
+        cudaStreamSetAttribute(c->stream, cudaStreamAttributeAccessPolicyWindow, &av);
+        cudaGetLastError();
+        c->l2_win_ptr = nullptr; c->l2_win_bytes = 0; c->l2_win_stream = nullptr;
+    }
+    c->stream = ns;
     return FLO_OK;
 }
 
@@ -274,7 +383,8 @@ extern "C" int flo_ctx_read_report(flo_ctx *c, uint32_t frame, uint32_t channel,
     if (!c || !out) { set_err("bad argument"); return FLO_ERR_ARG; }
     std::lock_guard<std::mutex> lk(c->mu);
     if (!c->report.p || frame >= c->report_frames || channel >= (uint32_t)REPORT_CH) { set_err("no report for frame %u channel %u", frame, channel); return FLO_ERR_ARG; }
-    CK(cudaSetDevice(c->device));
+    DeviceGuard dg(c->device);
+    CK(dg.err);
     const flo_cand_report *src = (const flo_cand_report *)c->report.p + ((size_t)frame * REPORT_CH + channel) * NCAND;
     CK(cudaMemcpy(out, src, sizeof(flo_cand_report) * NCAND, cudaMemcpyDeviceToHost));
     return FLO_OK;
@@ -361,6 +471,36 @@ extern "C" size_t flo_output_bound(const flo_track *tracks, size_t n_tracks) {
     return (size_t)L.out_bound;
 }
 
+// Host -> device copy of caller memory.  Page-locked sources go straight to the copy engine; pageable ones
+// (what a Rust &[f32] is) are staged through a ring of pinned slots filled by the copy threads, so the DMA of
+// one slot overlaps the host copy of the next instead of the driver's single-threaded bounce buffer.
+static cudaError_t h2d_from_caller(flo_ctx *c, void *dst, const void *src, size_t bytes, bool pinned, cudaStream_t st) {
+    if (pinned || bytes < (256u << 10) || getenv("FLO_B200_NO_STAGING")) return cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, st);
+    if (!c->stage.p) {
+        if (c->stage.reserve(STAGE_SLOTS * STAGE_SLOT_BYTES)) return cudaErrorMemoryAllocation;
+        if (!c->pool) c->pool = new CopyPool(copy_workers());
+    }
+    for (size_t off = 0; off < bytes; off += STAGE_SLOT_BYTES) {
+        const size_t len = std::min(STAGE_SLOT_BYTES, bytes - off);
+        const unsigned slot = c->stage_next++ % STAGE_SLOTS;
+        uint8_t *sp = (uint8_t *)c->stage.p + slot * STAGE_SLOT_BYTES;
+        cudaError_t e = cudaSuccess;
+        if (c->slot_used[slot]) e = cudaEventSynchronize(c->ev_slot[slot]);       // the DMA that last read this slot
+        if (e != cudaSuccess) return e;
+        c->pool->copy(sp, (const uint8_t *)src + off, len);
+        e = cudaMemcpyAsync((uint8_t *)dst + off, sp, len, cudaMemcpyHostToDevice, st);
+        if (e == cudaSuccess) e = cudaEventRecord(c->ev_slot[slot], st);
+        if (e != cudaSuccess) return e;
+        c->slot_used[slot] = true;
+    }
+    return cudaSuccess;
+}
+static bool is_pinned(const void *p) {
+    cudaPointerAttributes a;
+    if (cudaPointerGetAttributes(&a, p) != cudaSuccess) { cudaGetLastError(); return false; }
+    return a.type == cudaMemoryTypeHost || a.type == cudaMemoryTypeManaged;
+}
+
 // ---- the batch pass ----------------------------------------------------------------
 // `sink` (host entry only): when non-null and the batch is large, the images are copied to a pinned host block
 // while later waves are still being uploaded and encoded; *sink receives the block (its data is complete on return).
@@ -371,7 +511,8 @@ static int encode_batch_impl(flo_ctx *c, const flo_track *tracks, size_t n_track
     const bool convert = format == FLO_FMT_U8 || format == FLO_FMT_S32;     // pre-pass to f32, then the f32 path
     if (n_tracks == 0) return FLO_OK;
     if (level > 9) level = 9;                                          // with_compression, encoder.rs:26-29
-    CK(cudaSetDevice(c->device));
+    DeviceGuard dg(c->device);
+    CK(dg.err);
     Layout L;
     int rc = make_layout(tracks, n_tracks, format, L);
     if (rc) return rc;
@@ -537,9 +678,9 @@ static int encode_batch_impl(flo_ctx *c, const flo_track *tracks, size_t n_track
     CK(cudaEventRecord(c->ev[1], st));
     if (piped) { CK(cudaEventRecord(c->ev_fin, st)); CK(cudaStreamWaitEvent(s_in, c->ev_fin, 0)); }   // arenas are reused across calls
 
-    // per-wave D2H sink (few tracks only: header/TOC/metadata regions are copied one by one at the end)
+    // per-wave D2H sink (up to 256 tracks: header/TOC/metadata regions are copied one by one at the end)
     OutBlock *blk = nullptr;
-    const bool sink_on = sink && piped && n_tracks <= 16 && L.out_bound >= SMALL_OUTPUT;
+    const bool sink_on = sink && piped && n_tracks <= 256 && L.out_bound >= SMALL_OUTPUT;
     struct WaveEnd { unsigned long long excl; uint32_t size; uint32_t pad; };
     WaveEnd *h_wave = nullptr;
     if (sink_on) {
@@ -557,7 +698,9 @@ static int encode_batch_impl(flo_ctx *c, const flo_track *tracks, size_t n_track
 
     // track cursor for the per-wave sample copies
     size_t tcur = 0;
-    CK(cudaEventRecord(c->ev[2], st));
+    std::vector<bool> pinned_src;         // is the caller's buffer of track t page-locked? (asked once per track)
+    size_t pinned_known = 0;
+    { cudaError_t e = cudaEventRecord(c->ev[2], st); if (e != cudaSuccess) return fail(e, "event record failed"); }
     uint32_t g0 = 0;
     for (int w = 0; w < n_waves; w++) {
         const uint32_t g1 = wave_end[w];
@@ -571,9 +714,10 @@ static int encode_batch_impl(flo_ctx *c, const flo_track *tracks, size_t n_track
                 const uint64_t spf = (uint64_t)d.sample_rate * d.channels;
                 const uint64_t e_lo = (f_lo - d.first_frame) * spf;
                 const uint64_t e_hi = (f_hi == (uint64_t)d.first_frame + d.n_frames) ? d.n_inter : (f_hi - d.first_frame) * spf;
-                cudaError_t e = cudaMemcpyAsync((uint8_t *)c->in.p + L.in_off[t] + e_lo * esz,
+                if (t >= pinned_known) { pinned_src.resize(t + 1, false); for (size_t q = pinned_known; q <= t; q++) pinned_src[q] = is_pinned(tracks[q].samples); pinned_known = t + 1; }
+                cudaError_t e = h2d_from_caller(c, (uint8_t *)c->in.p + L.in_off[t] + e_lo * esz,
                                                 (const uint8_t *)tracks[t].samples + e_lo * esz, (e_hi - e_lo) * esz,
-                                                cudaMemcpyHostToDevice, s_in);
+                                                pinned_src[t], s_in);
                 if (e != cudaSuccess) return fail(e, "H2D of the samples failed");
                 if ((uint64_t)d.first_frame + d.n_frames <= g1) tcur = t + 1;
             }
@@ -604,16 +748,19 @@ static int encode_batch_impl(flo_ctx *c, const flo_track *tracks, size_t n_track
         }
         g0 = g1;
     }
-    CK(cudaEventRecord(c->ev[3], st));
-    CK(launch_toc(fp, st));
-    launches += NF ? 1 : 0;
-    CK(cudaEventRecord(c->ev[4], st));
-    CK(launch_crc_segments(fp, st));
-    launches += NSEG ? 1 : 0;
-    CK(cudaEventRecord(c->ev[5], st));
-    CK(launch_headers(fp, st));
-    launches += 1;
-    CK(cudaEventRecord(c->ev[6], st));
+    {
+        cudaError_t e = cudaEventRecord(c->ev[3], st);
+        if (e == cudaSuccess) e = launch_toc(fp, st);
+        launches += NF ? 1 : 0;
+        if (e == cudaSuccess) e = cudaEventRecord(c->ev[4], st);
+        if (e == cudaSuccess) e = launch_crc_segments(fp, st);
+        launches += NSEG ? 1 : 0;
+        if (e == cudaSuccess) e = cudaEventRecord(c->ev[5], st);
+        if (e == cudaSuccess) e = launch_headers(fp, st);
+        launches += 1;
+        if (e == cudaSuccess) e = cudaEventRecord(c->ev[6], st);
+        if (e != cudaSuccess) return fail(e, "finalise kernels failed");
+    }
 
     if (sink_on) {
         // DATA bytes of each wave leave the device as soon as its kernel is done, on their own stream
@@ -641,9 +788,12 @@ static int encode_batch_impl(flo_ctx *c, const flo_track *tracks, size_t n_track
     // results: per-track offsets/lengths + error flag
     uint64_t *h_off = (uint64_t *)(hs + align_up(sizeof(TrackDev) * n_tracks + L.meta_total, 16));
     uint32_t *h_err = (uint32_t *)(h_off + 2 * n_tracks);           // err + 8 counters
-    CK(cudaMemcpyAsync(h_off, c->foff.p, 16ull * n_tracks, cudaMemcpyDeviceToHost, st));
-    CK(cudaMemcpyAsync(h_err, ep.err, 4 * 47, cudaMemcpyDeviceToHost, st));   // err, counters[8], pad, phase clocks[16]
-    CK(cudaStreamSynchronize(st));
+    {
+        cudaError_t e = cudaMemcpyAsync(h_off, c->foff.p, 16ull * n_tracks, cudaMemcpyDeviceToHost, st);
+        if (e == cudaSuccess) e = cudaMemcpyAsync(h_err, ep.err, 4 * 47, cudaMemcpyDeviceToHost, st);   // err, counters[8], pad, phase clocks[16]
+        if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+        if (e != cudaSuccess) return fail(e, "reading back the batch results failed");
+    }
     if (*h_err) { if (blk) { cudaDeviceSynchronize(); drop_block(blk); } set_err("device-side consistency check failed (code 0x%08x)", *h_err); return FLO_ERR_INTERNAL; }
     for (size_t t = 0; t < n_tracks; t++) { offsets[t] = h_off[t]; lens[t] = h_off[n_tracks + t]; }
     for (int i = 0; i < 8; i++) c->counters[i] = h_err[1 + i];
@@ -817,7 +967,8 @@ int decode_impl(flo_ctx *c, const uint8_t *h_file, const void *d_file, size_t le
     *n_out = 0;
     if (out) *out = nullptr;
     std::lock_guard<std::mutex> lk(c->mu);
-    CK(cudaSetDevice(c->device));
+    DeviceGuard dg(c->device);
+    CK(dg.err);
     cudaStream_t st = c->stream;
     uint8_t head[80] = {0};
     const size_t have = len < 74 ? len : 74;

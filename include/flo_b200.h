@@ -92,7 +92,16 @@ int flo_encode_batch(flo_ctx *ctx, const flo_track *tracks, size_t n_tracks, int
  * written to the device buffer d_out (capacity >= flo_output_bound).  The
  * image of track i is d_out[offsets[i] .. offsets[i] + lens[i]); offsets/lens
  * are host arrays of n_tracks entries.  The call returns after the device
- * work finished. */
+ * work finished.
+ *
+ * Stream ordering (both device entries, encode and decode): the kernels run on
+ * the context's stream.  The context's own stream is a blocking stream, i.e. it
+ * is ordered after everything issued earlier on the legacy default stream (where
+ * torch's default stream runs), so inputs produced there need no extra
+ * synchronisation.  Inputs produced on ANY OTHER stream must either be complete
+ * (cudaStreamSynchronize / event wait) before the call, or that stream must be
+ * given to the context with flo_ctx_set_stream first.  Reading half-written
+ * input is not detected: the result would be a valid file of the wrong samples. */
 int flo_encode_batch_device(flo_ctx *ctx, const flo_track *tracks, size_t n_tracks, int format,
                             uint8_t level, void *d_out, size_t d_out_capacity,
                             uint64_t *offsets, uint64_t *lens);
@@ -101,7 +110,8 @@ int flo_encode_batch_device(flo_ctx *ctx, const flo_track *tracks, size_t n_trac
 size_t flo_output_bound(const flo_track *tracks, size_t n_tracks);
 
 /* Run the device work of this context on a caller-owned CUDA stream
- * (a cudaStream_t / CUstream passed as void*; NULL = the context's own). */
+ * (a cudaStream_t / CUstream passed as void*; NULL = the context's own): use the
+ * stream that produces the device inputs / consumes the device outputs. */
 int flo_ctx_set_stream(flo_ctx *ctx, void *cuda_stream);
 
 /* Timing of the last batch call, measured with CUDA events on the stream the
@@ -152,8 +162,10 @@ int flo_decode(flo_ctx *ctx, const uint8_t *file, size_t len, float **out, size_
 int flo_decode_device(flo_ctx *ctx, const void *d_file, size_t len, float *d_out, size_t d_out_capacity,
                       size_t *n_interleaved, flo_info *info);
 
-/* Pinned host memory (optional; speeds up the host<->device copies of
- * flo_encode / flo_encode_batch when inputs live in it). */
+/* Pinned host memory (optional).  Page-locked inputs go to the copy engine
+ * directly; pageable inputs (a plain Rust slice) are staged by the library
+ * through its own pinned ring with several copy threads (FLO_B200_COPY_THREADS
+ * overrides their number). */
 void *flo_host_alloc(size_t bytes);
 void  flo_host_free(void *p);
 

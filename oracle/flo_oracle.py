@@ -22,7 +22,7 @@ def build(force: bool = False) -> str:
     src = os.path.join(_HERE, "flo_oracle.c")
     hdr = os.path.join(_HERE, "flo_oracle.h")
     stale = (not os.path.exists(_SO)) or any(
-        os.path.exists(p) and os.path.getmtime(p) > os.path.getmtime(_SO) for p in (src, hdr)
+        os.path.exists(p) and os.path.getmtime(p) > os.path.getmtime(_SO) for p in (src, hdr, os.path.join(_HERE, "Makefile"))
     )
     if force or stale:
         subprocess.check_call(["make", "-C", _HERE, "-s", "-B", "libflo_oracle.so"])
