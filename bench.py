@@ -10,7 +10,7 @@ A step = one pass of the whole encode path over one batch of synthetic PCM.  Wor
   3 (default at N > 1): batch corpus of 3-minute 44.1 kHz stereo tracks sharded over ranks, weak scaling:
       every rank encodes --tracks (default 20) x 180 s per step; no collective on the data path, one
       all_gather of per-rank byte lengths per step for the final concatenation.
-  4: hi-res 96 kHz stereo sweep+noise, bit_depth 24 in the header, level 9 (maximum LPC order), 600 s.
+  4: hi-res 96 kHz stereo sweep+noise, bit_depth 24 in the header, level 9 (maximum LPC order), --seconds long.
   5: 8 kHz mono speech-like signal, 4096 tracks of 8 s (small frames), level 5.
 Every workload enters through Encoder::encode's documented input (interleaved f32).
 `value` = PCM GB/s (2 bytes x interleaved samples / time; 3 bytes for the nominal 24-bit config 4) over all
@@ -57,7 +57,7 @@ def track_lengths(cfg_id: int, args, world: int) -> list[int]:
     if cfg_id == 3:
         return [180 * c["sr"]] * (args.tracks * world)
     if cfg_id == 4:
-        return [min(args.seconds, 600) * c["sr"]] * world
+        return [args.seconds * c["sr"]] * world
     return [8 * c["sr"]] * (4096 * world)
 
 
@@ -433,7 +433,7 @@ def main() -> int:
 
         # the other BASELINE configs, device-resident (their own bench lines: bench.py --config 3|4|5)
         extras["configs"] = {}
-        for cid, kw in ((3, dict(tracks=20)), (4, dict(seconds=600)), (5, dict())):
+        for cid, kw in ((3, dict(tracks=20)), (4, dict(seconds=1184)), (5, dict())):
             cc = CONFIGS[cid]
 
             lens = track_lengths(cid, argparse.Namespace(seconds=kw.get("seconds", 3600), tracks=kw.get("tracks", 20)), 1)

@@ -65,6 +65,7 @@ struct ChanState {
     double qd[NLPC][MAXORD];          // q / 2^shift as f64 (exact), for the FP64-pipe FIR
     i32 qc[NLPC][MAXORD];             // quantised coefficients (lpc.rs:263-273)
     i32 lpc_ok[NLPC];
+    i32 lpc_run[NLPC];                // orders pass 2 evaluates in its current run (a second run redoes window misses)
     i32 lpc_shift[NLPC];
     i32 lpc_j0[NLPC];                 // guessed shift window {j0, j0 + 1} for sum(w >> j)
     double lpc_err[NLPC];             // prediction error after each order (window guess only)
@@ -105,6 +106,7 @@ struct Smem {
     u64 partT[GROUP][NLPC][2][NWARP]; // pass 2: sum(w >> j0), sum(w >> (j0 + 1)) per region
     u64 partS[GROUP][NCAND][NWARP];   // pass 3: exact sum(w >> j) per region
     u32 edge[GROUP][NWARP + 1];       // packer: bits of the words shared by two regions, by boundary
+    i32 redo[GROUP];                  // a channel asks for the second run of pass 2
 };
 // dynamic shared memory: Smem | work area (ingest stages, then the packer's staging ring) | sample planes
 constexpr size_t SMEM_HDR = (sizeof(Smem) + 127) & ~size_t(127);
@@ -624,7 +626,7 @@ struct Sweeps {
             constexpr bool PAIR = LO < HI && HI + LO <= 13;
             constexpr int OA = HI, OB = PAIR ? LO : 0;
             constexpr int BS = PAIR ? FLO_PAIR_BS : 4;
-            const bool oka = cs.lpc_ok[OA - 5] != 0, okb = OB > 0 && cs.lpc_ok[(OB > 0 ? OB : 5) - 5] != 0;
+            const bool oka = cs.lpc_run[OA - 5] != 0, okb = OB > 0 && cs.lpc_run[(OB > 0 ? OB : 5) - 5] != 0;
             if (oka || okb) {
                 LpcStat a = st[OA - lo0], b = st[(OB > 0 ? OB : OA) - lo0];
                 const int j0a = cs.lpc_j0[OA - 5], j0b = cs.lpc_j0[(OB > 0 ? OB : OA) - 5];
@@ -645,8 +647,8 @@ struct Sweeps {
                         if (j & 1) { b.sum += pba + aa; b.orr |= pba | aa; b.t0 += pbw + ws; b.t1 += pbv + wv; }
                         else { pba = aa; pbw = ws; pbv = wv; }
                     });
-                st[OA - lo0] = a;
-                if constexpr (OB > 0) st[OB - lo0] = b;
+                if (oka) st[OA - lo0] = a;
+                if constexpr (OB > 0) { if (okb) st[OB - lo0] = b; }
             }
             Sweeps<NH, PAIR ? LO + 1 : LO, HI - 1>::run(cs, x, st, lo0);
         }
@@ -674,7 +676,7 @@ __device__ void pass2_range(Smem &s, int nch) {
             const ChanState &cs = s.cs[c];
 #pragma unroll
             for (int O = LO; O <= HI; O++) {
-                if (cs.lpc_ok[O - 5]) {
+                if (cs.lpc_run[O - 5]) {
                     const i32 r = lpc_residual_at(cs, win, O, i);
                     const u32 a = (u32)abs(r);
                     const u32 ws = (a + (u32)(r >> 31)) >> cs.lpc_j0[O - 5];
@@ -859,15 +861,21 @@ __device__ void after_pass1_warp(ChanState &cs, int fmax, bool lpc_on) {
         if (lane < NLPC && cs.n <= 5 + lane) cs.lpc_ok[lane] = 0;                 // encoder.rs:255-257
     }
     __syncwarp();
+    if (lane < NLPC) cs.lpc_run[lane] = cs.lpc_ok[lane];
+    __syncwarp();
 }
 
-// after pass 2 (lanes 6..13): resolve the LPC candidates (encoder.rs:262-286)
-__device__ void after_pass2_warp(ChanState &cs, int P, u32 *counters) {
+// after pass 2 (lanes 6..13): resolve the LPC candidates (encoder.rs:262-286).  A candidate whose Rice parameter
+// fell outside the guessed shift window is sized by a second run of pass 2 with the window moved onto it (`redo`
+// true: the run mask and the zeroed sums are set up for that run; the k of a candidate does not depend on the
+// window, so the second run always hits).  Returns whether any order of the channel asks for the second run.
+__device__ bool after_pass2_warp(Smem &s, int c, int P, bool redo, u32 *counters) {
+    ChanState &cs = s.cs[c];
     const int lane = threadIdx.x & 31;
     const u32 n = (u32)cs.n;
     bool hit = false, miss = false;
     const int o = lane - 1;
-    if (lane >= 6 && o <= P && cs.lpc_ok[o - 5]) {
+    if (lane >= 6 && o <= P && cs.lpc_ok[o - 5] && cs.lpc_run[o - 5]) {
         const int i = o - 5;
         const u32 orr = cs.l_or[i];
         const int bl = bitlen32(orr);
@@ -884,7 +892,7 @@ __device__ void after_pass2_warp(ChanState &cs, int P, u32 *counters) {
                 hit = true;
             } else {
                 cs.cand_state[lane] = CS_BOUNDED;                                 // window miss or 2^19 <= max|r| < 2^20
-                miss = true;
+                miss = bl <= 19;
             }
         }
     }
@@ -893,7 +901,19 @@ __device__ void after_pass2_warp(ChanState &cs, int P, u32 *counters) {
         if (hm) atomicAdd(counters + 2, (u32)__popc(hm));
         if (mm) atomicAdd(counters + 3, (u32)__popc(mm));
     }
+    if (lane >= 6 && lane < 6 + NLPC) {
+        const int i = lane - 6;
+        const bool again = redo && miss;
+        cs.lpc_run[i] = again ? 1 : 0;
+        if (again) {
+            const int k = cs.cand_k[lane];
+            cs.lpc_j0[i] = k >= 1 ? k - 1 : 0;
+            cs.l_sum[i] = 0; cs.l_or[i] = 0; cs.l_t0[i] = 0; cs.l_t1[i] = 0;
+            for (int w = 0; w < NWARP; w++) { s.partA[c][lane][w] = 0; s.partT[c][i][0][w] = 0; s.partT[c][i][1][w] = 0; }
+        }
+    }
     __syncwarp();
+    return redo && mm != 0;
 }
 
 __device__ __forceinline__ u64 warp_min64(u64 v) {
@@ -1627,7 +1647,9 @@ __global__ void __launch_bounds__(NT, FLO_VARIANT_CTAS) k_encode_frames(const En
                 for (int l = 0; l <= MAXORD; l++) cs.ac[l] = 0;
                 for (int o = 0; o < NLPC; o++) { cs.l_sum[o] = 0; cs.l_or[o] = 0; cs.l_t0[o] = 0; cs.l_t1[o] = 0; cs.lpc_ok[o] = 0; }
                 cs.ex_cand = -1; cs.ex_s = 0; cs.ex_max = 0; cs.ex_fixed = 0;
+                s.redo[tid] = 0;
             }
+            if (tid == 1 && nch == 1) s.redo[1] = 0;
             __syncthreads();
             PH(const long long ta0 = clock64();)
             bool any_lpc = false;
@@ -1650,11 +1672,19 @@ __global__ void __launch_bounds__(NT, FLO_VARIANT_CTAS) k_encode_frames(const En
                 __syncthreads();
             }
             PH(const long long ta3 = clock64();)
-            if ((tid >> 5) < nch && s.cs[tid >> 5].n > 0) {
-                ChanState &cs = s.cs[tid >> 5];
-                if (run2) after_pass2_warp(cs, P, s.cnt);
-                next_open_candidate_warp(cs, prune, s.cnt);
+            if ((tid >> 5) < nch && s.cs[tid >> 5].n > 0 && run2) {
+                const bool again = after_pass2_warp(s, tid >> 5, P, true, s.cnt);
+                if ((tid & 31) == 0 && again) s.redo[tid >> 5] = 1;
             }
+            __syncthreads();
+            if (run2 && (s.redo[0] | s.redo[nch - 1])) {
+                // second run of pass 2 for the candidates whose Rice parameter missed the guessed window
+                if constexpr (P > 0) pass2<P>(s, nch);
+                __syncthreads();
+                if ((tid >> 5) < nch && s.cs[tid >> 5].n > 0) after_pass2_warp(s, tid >> 5, P, false, s.cnt);
+                __syncthreads();
+            }
+            if ((tid >> 5) < nch && s.cs[tid >> 5].n > 0) next_open_candidate_warp(s.cs[tid >> 5], prune, s.cnt);
             __syncthreads();
             // exact evaluation of whatever is still open (bounded candidates that can still win)
             for (;;) {
