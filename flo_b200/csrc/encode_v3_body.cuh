@@ -65,7 +65,6 @@ struct ChanState {
     double qd[NLPC][MAXORD];          // q / 2^shift as f64 (exact), for the FP64-pipe FIR
     i32 qc[NLPC][MAXORD];             // quantised coefficients (lpc.rs:263-273)
     i32 lpc_ok[NLPC];
-    i32 lpc_run[NLPC];                // orders pass 2 evaluates in its current run (a second run redoes window misses)
     i32 lpc_shift[NLPC];
     i32 lpc_j0[NLPC];                 // guessed shift window {j0, j0 + 1} for sum(w >> j)
     double lpc_err[NLPC];             // prediction error after each order (window guess only)
@@ -107,6 +106,11 @@ struct Smem {
     u64 partS[GROUP][NCAND][NWARP];   // pass 3: exact sum(w >> j) per region
     u32 edge[GROUP][NWARP + 1];       // packer: bits of the words shared by two regions, by boundary
     i32 redo[GROUP];                  // a channel asks for the second run of pass 2
+    // CRC32 of the frame's bytes (crc32.rs): tables staged from global memory once per CTA
+    u32 crc_x[4][256];                // v -> v * x^(32 NT) mod p, by byte of v (the strided Horner step)
+    u32 crc_klane[NT];                // x^(32 (NT - t)) mod p
+    u32 crc_slice0[256];              // the byte-wise table of crc32.rs:2-20
+    u32 fcrc;                         // raw CRC state of the current frame, XORed together by the warps
 };
 // dynamic shared memory: Smem | work area (ingest stages, then the packer's staging ring) | sample planes
 constexpr size_t SMEM_HDR = (sizeof(Smem) + 127) & ~size_t(127);
@@ -626,7 +630,7 @@ struct Sweeps {
             constexpr bool PAIR = LO < HI && HI + LO <= 13;
             constexpr int OA = HI, OB = PAIR ? LO : 0;
             constexpr int BS = PAIR ? FLO_PAIR_BS : 4;
-            const bool oka = cs.lpc_run[OA - 5] != 0, okb = OB > 0 && cs.lpc_run[(OB > 0 ? OB : 5) - 5] != 0;
+            const bool oka = cs.lpc_ok[OA - 5] != 0, okb = OB > 0 && cs.lpc_ok[(OB > 0 ? OB : 5) - 5] != 0;
             if (oka || okb) {
                 LpcStat a = st[OA - lo0], b = st[(OB > 0 ? OB : OA) - lo0];
                 const int j0a = cs.lpc_j0[OA - 5], j0b = cs.lpc_j0[(OB > 0 ? OB : OA) - 5];
@@ -647,8 +651,8 @@ struct Sweeps {
                         if (j & 1) { b.sum += pba + aa; b.orr |= pba | aa; b.t0 += pbw + ws; b.t1 += pbv + wv; }
                         else { pba = aa; pbw = ws; pbv = wv; }
                     });
-                if (oka) st[OA - lo0] = a;
-                if constexpr (OB > 0) { if (okb) st[OB - lo0] = b; }
+                st[OA - lo0] = a;
+                if constexpr (OB > 0) st[OB - lo0] = b;
             }
             Sweeps<NH, PAIR ? LO + 1 : LO, HI - 1>::run(cs, x, st, lo0);
         }
@@ -676,7 +680,7 @@ __device__ void pass2_range(Smem &s, int nch) {
             const ChanState &cs = s.cs[c];
 #pragma unroll
             for (int O = LO; O <= HI; O++) {
-                if (cs.lpc_run[O - 5]) {
+                if (cs.lpc_ok[O - 5]) {
                     const i32 r = lpc_residual_at(cs, win, O, i);
                     const u32 a = (u32)abs(r);
                     const u32 ws = (a + (u32)(r >> 31)) >> cs.lpc_j0[O - 5];
@@ -861,26 +865,26 @@ __device__ void after_pass1_warp(ChanState &cs, int fmax, bool lpc_on) {
         if (lane < NLPC && cs.n <= 5 + lane) cs.lpc_ok[lane] = 0;                 // encoder.rs:255-257
     }
     __syncwarp();
-    if (lane < NLPC) cs.lpc_run[lane] = cs.lpc_ok[lane];
-    __syncwarp();
 }
 
-// after pass 2 (lanes 6..13): resolve the LPC candidates (encoder.rs:262-286).  A candidate whose Rice parameter
-// fell outside the guessed shift window is sized by a second run of pass 2 with the window moved onto it (`redo`
-// true: the run mask and the zeroed sums are set up for that run; the k of a candidate does not depend on the
-// window, so the second run always hits).  Returns whether any order of the channel asks for the second run.
+// after pass 2 (lanes 6..13): resolve the LPC candidates (encoder.rs:262-286).  When the Rice parameter of a
+// candidate fell outside the guessed shift window, pass 2 runs a second time with the window moved onto it
+// (`redo` true: the windows and the zeroed sums of the channel are set up for that run; the k of a candidate does
+// not depend on the window, so the second run always hits).  Returns whether the channel asks for the second run.
 __device__ bool after_pass2_warp(Smem &s, int c, int P, bool redo, u32 *counters) {
     ChanState &cs = s.cs[c];
     const int lane = threadIdx.x & 31;
     const u32 n = (u32)cs.n;
     bool hit = false, miss = false;
     const int o = lane - 1;
-    if (lane >= 6 && o <= P && cs.lpc_ok[o - 5] && cs.lpc_run[o - 5]) {
+    const bool mine = lane >= 6 && o <= P && cs.lpc_ok[o - 5];
+    int k = 0;
+    if (mine) {
         const int i = o - 5;
         const u32 orr = cs.l_or[i];
         const int bl = bitlen32(orr);
         if (bl < 21) {                                                            // else max|r| >= 2^20 > 1_000_000: rejected
-            const int k = rice_k_or(orr, cs.l_sum[i], n);
+            k = rice_k_or(orr, cs.l_sum[i], n);
             cs.cand_k[lane] = k;
             cs.cand_sumabs[lane] = cs.l_sum[i];
             const int jj = k >= 1 ? k - 1 : 0;
@@ -901,19 +905,16 @@ __device__ bool after_pass2_warp(Smem &s, int c, int P, bool redo, u32 *counters
         if (hm) atomicAdd(counters + 2, (u32)__popc(hm));
         if (mm) atomicAdd(counters + 3, (u32)__popc(mm));
     }
-    if (lane >= 6 && lane < 6 + NLPC) {
-        const int i = lane - 6;
-        const bool again = redo && miss;
-        cs.lpc_run[i] = again ? 1 : 0;
-        if (again) {
-            const int k = cs.cand_k[lane];
-            cs.lpc_j0[i] = k >= 1 ? k - 1 : 0;
-            cs.l_sum[i] = 0; cs.l_or[i] = 0; cs.l_t0[i] = 0; cs.l_t1[i] = 0;
-            for (int w = 0; w < NWARP; w++) { s.partA[c][lane][w] = 0; s.partT[c][i][0][w] = 0; s.partT[c][i][1][w] = 0; }
-        }
+    const bool again = redo && mm != 0;
+    if (again && mine) {
+        const int i = o - 5;
+        if (miss) cs.lpc_j0[i] = k >= 1 ? k - 1 : 0;
+        cs.l_sum[i] = 0; cs.l_or[i] = 0; cs.l_t0[i] = 0; cs.l_t1[i] = 0;
+        cs.cand_state[lane] = CS_ABSENT;
+        for (int w = 0; w < NWARP; w++) { s.partA[c][lane][w] = 0; s.partT[c][i][0][w] = 0; s.partT[c][i][1][w] = 0; }
     }
     __syncwarp();
-    return redo && mm != 0;
+    return again;
 }
 
 __device__ __forceinline__ u64 warp_min64(u64 v) {
@@ -1521,6 +1522,65 @@ __device__ __forceinline__ void prefetch_frame_l2(const EncodeParams &p, u32 g) 
 }
 
 // ----------------------------------------------------------------------------
+// CRC32 of the frame just written (crc32.rs:23-30; the DATA chunk's CRC is folded from the frames' by
+// k_crc_frames).  Raw CRC R(M) = M(x) x^32 mod p: linear, ignores leading zeros.  Thread t of the CTA reads the
+// aligned words t, t + NT, ... of the frame (coalesced; the bytes were written by this CTA a moment ago and come
+// from L2, eight loads in flight per thread) and runs d = d x^(32 NT) + w -- four table look-ups, like
+// slice-by-4.  The words are aligned to the END of the frame, so thread t's stream weighs x^(32 (NT - t)) whatever
+// the frame's length; the XOR over the threads is the state after the last whole word, and the <= 3 bytes behind
+// it are added byte-wise.  multmodp follows zlib's crc32_combine helper (zlib 1.2.12+, crc32.c; (C) 1995-2022
+// Mark Adler, zlib licence), re-typed for the reflected polynomial.
+// ----------------------------------------------------------------------------
+__device__ __forceinline__ u32 crc_multmodp(u32 a, u32 b) {
+    u32 m = 1u << 31, p = 0;
+    for (;;) {
+        if (a & m) { p ^= b; if ((a & (m - 1)) == 0) break; }
+        m >>= 1;
+        b = (b & 1) ? (b >> 1) ^ 0xEDB88320u : b >> 1;
+    }
+    return p;
+}
+// raw CRC of the bytes [a, a + fsize) of p.out -> p.frame_crc[g]; the bytes must be visible (barrier before)
+__device__ __noinline__ void crc_frame(Smem &s, const EncodeParams &p, u32 g, u64 a, u32 fsize) {
+    const int tid = threadIdx.x;
+    const uint8_t *out = p.out;
+    const u64 b = a + fsize, b4 = b & ~3ull;
+    if (b4 > a) {
+        const u64 a4 = a & ~3ull;
+        const u64 nwords = (b4 - a4) >> 2;
+        const u64 J = (nwords + NT - 1) / NT;
+        const i64 s0 = (i64)b4 - (i64)(4ull * NT * J);       // may lie before a4: those words count as zero
+        const u32 head_mask = 0xFFFFFFFFu << (8 * (u32)(a - a4));
+        u32 d = 0;
+        i64 addr = s0 + 4 * (i64)tid;
+        for (u64 j = 0; j < J; j += 8) {
+            u32 w[8];
+#pragma unroll
+            for (int q = 0; q < 8; q++) {
+                const i64 aq = addr + (i64)q * 4 * NT;
+                w[q] = (j + q < J && aq >= (i64)a4) ? __ldcg(reinterpret_cast<const u32 *>(out + aq)) : 0u;
+                if (aq == (i64)a4) w[q] &= head_mask;
+            }
+#pragma unroll
+            for (int q = 0; q < 8; q++)
+                if (j + q < J) d = s.crc_x[0][d & 0xff] ^ s.crc_x[1][(d >> 8) & 0xff] ^ s.crc_x[2][(d >> 16) & 0xff] ^ s.crc_x[3][d >> 24] ^ w[q];
+            addr += 8ll * 4 * NT;
+        }
+        u32 c = crc_multmodp(s.crc_klane[tid], d);
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) c ^= __shfl_xor_sync(0xffffffffu, c, o);
+        if ((tid & 31) == 0 && c) atomicXor(&s.fcrc, c);
+    }
+    __syncthreads();
+    if (tid == 0) {
+        u32 c = s.fcrc;
+        for (u64 i = b4 > a ? b4 : a; i < b; i++) c = (c >> 8) ^ s.crc_slice0[(c ^ __ldcg(out + i)) & 0xff];
+        p.frame_crc[g] = c;
+        s.fcrc = 0;
+    }
+}
+
+// ----------------------------------------------------------------------------
 // the frame-encode kernel
 // ----------------------------------------------------------------------------
 extern __shared__ __align__(128) unsigned char dyn_smem[];
@@ -1534,7 +1594,11 @@ __global__ void __launch_bounds__(NT, FLO_VARIANT_CTAS) k_encode_frames(const En
     const int tid = threadIdx.x;
     LV(g_lev_phase = p.phase_cycles;)
     if (tid < 8) s.cnt[tid] = 0;
+    for (int i = tid; i < 1024; i += NT) (&s.crc_x[0][0])[i] = p.crc_tab[crc_tab_offset(NT) + i];
+    s.crc_klane[tid] = p.crc_tab[crc_tab_offset(NT) + 1024 + tid];
+    for (int i = tid; i < 256; i += NT) s.crc_slice0[i] = p.crc_tab[i];
     if (tid == 0) {
+        s.fcrc = 0;
         for (int i = 0; i < MAX_STAGES; i++) mbar_init(smem_u32(&s.bar_full[i]), 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
@@ -1602,6 +1666,8 @@ __global__ void __launch_bounds__(NT, FLO_VARIANT_CTAS) k_encode_frames(const En
             uint8_t *o = p.out + data_base + s.frame_excl;
             if (tid == 0) { o[0] = 0; put_u32le(o + 1, frame_samples); o[5] = 0; }
             for (u32 i = tid; i < 4 * C; i += NT) o[6 + i] = 0;
+            __syncthreads();
+            crc_frame(s, p, g, data_base + s.frame_excl, fsize);
             if (p.report) {
                 for (u32 i = tid; i < REPORT_CH * NCAND; i += NT) {
                     flo_cand_report *r = p.report + (size_t)g * REPORT_CH * NCAND + i;
@@ -1667,23 +1733,30 @@ __global__ void __launch_bounds__(NT, FLO_VARIANT_CTAS) k_encode_frames(const En
             bool run2 = false;
             for (int q = 0; q < nch; q++)
                 for (int o = 0; o < NLPC; o++) run2 |= s.cs[q].n > 0 && s.cs[q].lpc_ok[o] != 0;
-            if (run2) {
+            PH(long long ta3 = 0;)
+            for (int run = 0; run2 && run < 2; run++) {
                 if constexpr (P > 0) pass2<P>(s, nch);
                 __syncthreads();
-            }
-            PH(const long long ta3 = clock64();)
-            if ((tid >> 5) < nch && s.cs[tid >> 5].n > 0 && run2) {
-                const bool again = after_pass2_warp(s, tid >> 5, P, true, s.cnt);
-                if ((tid & 31) == 0 && again) s.redo[tid >> 5] = 1;
-            }
-            __syncthreads();
-            if (run2 && (s.redo[0] | s.redo[nch - 1])) {
-                // second run of pass 2 for the candidates whose Rice parameter missed the guessed window
-                if constexpr (P > 0) pass2<P>(s, nch);
+                PH(if (run == 0) ta3 = clock64();)
+                if ((tid >> 5) < nch && s.cs[tid >> 5].n > 0) {
+                    const bool again = after_pass2_warp(s, tid >> 5, P, run == 0, s.cnt);
+                    if ((tid & 31) == 0 && again) s.redo[tid >> 5] = 1;
+                }
                 __syncthreads();
-                if ((tid >> 5) < nch && s.cs[tid >> 5].n > 0) after_pass2_warp(s, tid >> 5, P, false, s.cnt);
+                if (run == 1 || !(s.redo[0] | s.redo[nch - 1])) break;
+                // second run of pass 2; a channel of the group that had no miss redoes its sums, too (same windows)
+                if ((tid >> 5) < nch && s.cs[tid >> 5].n > 0 && !s.redo[tid >> 5]) {
+                    ChanState &cs = s.cs[tid >> 5];
+                    const int lane = tid & 31, i = lane - 6;
+                    if (i >= 0 && i < NLPC && cs.lpc_ok[i]) {
+                        cs.l_sum[i] = 0; cs.l_or[i] = 0; cs.l_t0[i] = 0; cs.l_t1[i] = 0;
+                        cs.cand_state[lane] = CS_ABSENT;
+                        for (int w = 0; w < NWARP; w++) { s.partA[tid >> 5][lane][w] = 0; s.partT[tid >> 5][i][0][w] = 0; s.partT[tid >> 5][i][1][w] = 0; }
+                    }
+                }
                 __syncthreads();
             }
+            PH(if (!run2) ta3 = clock64();)
             if ((tid >> 5) < nch && s.cs[tid >> 5].n > 0) next_open_candidate_warp(s.cs[tid >> 5], prune, s.cnt);
             __syncthreads();
             // exact evaluation of whatever is still open (bounded candidates that can still win)
@@ -1872,6 +1945,8 @@ __global__ void __launch_bounds__(NT, FLO_VARIANT_CTAS) k_encode_frames(const En
             }
         }
         if (tid == 0 && pos - fpos != fsize) atomicExch(p.err, 0xBAD00002u);
+        __syncthreads();
+        crc_frame(s, p, g, fpos, fsize);
         PH(if (tid == 0) {
             const long long tc4 = clock64();
             atomicAdd(p.phase_cycles + 0, (u64)(tc1 - tc0)); atomicAdd(p.phase_cycles + 1, (u64)(tc2 - tc1));

@@ -240,6 +240,7 @@ struct flo_ctx {
     DevBuf in, out, meta, tracks, frames, ctrl, fexcl, fsize, foff, plane, cres, report;
     DevBuf dec_frames, dec_units, dec_base, dec_ctl;      // decoder scratch
     DevBuf conv;                                           // f32 samples of the U8 / S32 ingest pre-pass
+    DevBuf crc_tab, fcrc;                                  // CRC tables for the encode kernel; raw CRC of every frame
     uint64_t counters[24] = {0};      // [0..7] analysis counters, [8..23] per-phase SM clock sums
     HostBuf h_small, h_out;
     HostBuf stage;                                         // pinned ring for pageable caller buffers
@@ -299,6 +300,13 @@ extern "C" int flo_ctx_create(int device, flo_ctx **out) {
     for (auto &ev : c->ev_slot) cudaEventCreateWithFlags(&ev, cudaEventDisableTiming);
     cudaEventCreateWithFlags(&c->ev_fin, cudaEventDisableTiming);
     upload_crc_tables();
+    {
+        static uint32_t tab[CRC_TAB_WORDS];
+        crc_tables_host(tab);
+        if (c->crc_tab.reserve(sizeof tab) || cudaMemcpy(c->crc_tab.p, tab, sizeof tab, cudaMemcpyHostToDevice) != cudaSuccess) {
+            set_err("CRC table upload failed"); flo_ctx_destroy(c); return FLO_ERR_CUDA;
+        }
+    }
     for (int th : {512, 256, 128}) {
         e2 = encode_variant(th).configure(c->smem_optin / encode_variant(th).ctas_per_sm - (encode_variant(th).ctas_per_sm > 1 ? 1024 : 0));
         if (e2 != cudaSuccess) { set_err("cudaFuncSetAttribute(max dynamic smem): %s", cudaGetErrorString(e2)); flo_ctx_destroy(c); return FLO_ERR_CUDA; }
@@ -323,7 +331,7 @@ extern "C" void flo_ctx_destroy(flo_ctx *c) {
     }
     if (c->persist_prev != (size_t)-1) { cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, c->persist_prev); cudaGetLastError(); }
     for (DevBuf *b : {&c->in, &c->out, &c->meta, &c->tracks, &c->frames, &c->ctrl, &c->fexcl, &c->fsize,
-                      &c->foff, &c->plane, &c->cres, &c->report, &c->dec_frames, &c->dec_units, &c->dec_base, &c->dec_ctl, &c->conv})
+                      &c->foff, &c->plane, &c->cres, &c->report, &c->crc_tab, &c->fcrc, &c->dec_frames, &c->dec_units, &c->dec_base, &c->dec_ctl, &c->conv})
         b->release();
     c->h_small.release();
     c->h_out.release();
@@ -540,6 +548,7 @@ static int encode_batch_impl(flo_ctx *c, const flo_track *tracks, size_t n_track
     if ((rc = c->ctrl.reserve(ctrl_bytes))) return rc;
     if ((rc = c->fexcl.reserve(8ull * std::max<uint64_t>(NF, 1)))) return rc;
     if ((rc = c->fsize.reserve(4ull * std::max<uint64_t>(NF, 1)))) return rc;
+    if ((rc = c->fcrc.reserve(4ull * std::max<uint64_t>(NF, 1)))) return rc;
     if ((rc = c->foff.reserve(16ull * n_tracks))) return rc;
     if ((rc = c->meta.reserve(std::max<uint64_t>(L.meta_total, 1)))) return rc;
     if ((rc = c->h_small.reserve(sizeof(TrackDev) * n_tracks + L.meta_total + 16ull * n_tracks + 256))) return rc;
@@ -662,6 +671,8 @@ static int encode_batch_impl(flo_ctx *c, const flo_track *tracks, size_t n_track
     ep.report = c->report_on ? (flo_cand_report *)c->report.p : nullptr;
     ep.smem_plane_bytes = (uint32_t)plane_cap;
     ep.work_bytes = (uint32_t)work;
+    ep.crc_tab = (const uint32_t *)c->crc_tab.p;
+    ep.frame_crc = (uint32_t *)c->fcrc.p;
     ep.stagger = getenv("FLO_B200_STAGGER") ? (uint32_t)atoi(getenv("FLO_B200_STAGGER")) : 0u;
 
     FinalParams fp;
@@ -670,6 +681,7 @@ static int encode_batch_impl(flo_ctx *c, const flo_track *tracks, size_t n_track
     fp.out = out; fp.meta = (const uint8_t *)c->meta.p;
     fp.frame_excl = ep.frame_excl; fp.frame_size = ep.frame_size;
     fp.track_crc = ctl + 48; fp.n_segs = NSEG;
+    fp.frame_crc = (const uint32_t *)c->fcrc.p;
     fp.file_off = (unsigned long long *)c->foff.p;
     fp.file_len = fp.file_off + n_tracks;
 
@@ -753,8 +765,8 @@ static int encode_batch_impl(flo_ctx *c, const flo_track *tracks, size_t n_track
         if (e == cudaSuccess) e = launch_toc(fp, st);
         launches += NF ? 1 : 0;
         if (e == cudaSuccess) e = cudaEventRecord(c->ev[4], st);
-        if (e == cudaSuccess) e = launch_crc_segments(fp, st);
-        launches += NSEG ? 1 : 0;
+        if (e == cudaSuccess) e = launch_crc_frames(fp, st);
+        launches += NF ? 1 : 0;
         if (e == cudaSuccess) e = cudaEventRecord(c->ev[5], st);
         if (e == cudaSuccess) e = launch_headers(fp, st);
         launches += 1;
@@ -907,6 +919,68 @@ extern "C" int flo_encode(flo_ctx *c, const float *samples, size_t n, uint32_t s
 extern "C" int flo_encode_pcm16(flo_ctx *c, const int16_t *pcm, size_t n, uint32_t sr, uint8_t ch, uint8_t bits,
                                 uint8_t level, const uint8_t *meta, size_t meta_len, uint8_t **out, size_t *out_len) {
     return encode_one(c, pcm, n, FLO_FMT_PCM16, sr, ch, bits, level, meta, meta_len, out, out_len);
+}
+
+// ------------------------------------------------------------------------------------------------
+// StreamingEncoder::encode_frame_data (libflo/src/streaming/encoder.rs:216-257) for a run of frames
+// ------------------------------------------------------------------------------------------------
+// The reference encodes one frame with Encoder::encode, reads the one-frame file back (Reader) and writes every
+// channel again as [rice_parameter][coefficients as i32 LE][residual bytes] (serialize_channel, :243-257).
+// Frames are independent in the encoder (encoder.rs:53-61), so frame g of the file of the whole run holds the
+// bytes a one-frame file of second g would hold: the run goes through ONE device pass and the frames are
+// re-serialised here, on the host, from that image (what Reader::read_channel_data reads, reader.rs:168-247).
+extern "C" int flo_stream_encode_frames(flo_ctx *c, const float *samples, size_t n, uint32_t sr, uint8_t ch, uint8_t bits,
+                                        uint8_t level, uint8_t **out, size_t *out_len, uint64_t **frame_off, uint32_t *n_frames) {
+    if (!out || !out_len || !frame_off || !n_frames) { set_err("bad argument"); return FLO_ERR_ARG; }
+    *out = nullptr; *out_len = 0; *frame_off = nullptr; *n_frames = 0;
+    uint8_t *img = nullptr;
+    size_t img_len = 0;
+    int rc = encode_one(c, samples, n, FLO_FMT_F32, sr, ch, bits, level, nullptr, 0, &img, &img_len);
+    if (rc) return rc;
+    auto rd32 = [&](size_t p) { return (uint32_t)img[p] | ((uint32_t)img[p + 1] << 8) | ((uint32_t)img[p + 2] << 16) | ((uint32_t)img[p + 3] << 24); };
+    const uint32_t nf = img_len >= 74 ? rd32(70) : 0;
+    const size_t data0 = 74 + 20ull * nf;
+    // the re-serialised frame is never longer than the frame itself
+    uint8_t *buf = (uint8_t *)malloc(img_len > data0 ? img_len - data0 + 16 : 16);
+    uint64_t *offs = (uint64_t *)malloc(sizeof(uint64_t) * ((size_t)nf + 1));
+    if (!buf || !offs) { free(buf); free(offs); flo_free(img); set_err("out of host memory"); return FLO_ERR_NOMEM; }
+    auto wr32 = [&](uint8_t *p, uint32_t v) { p[0] = (uint8_t)v; p[1] = (uint8_t)(v >> 8); p[2] = (uint8_t)(v >> 16); p[3] = (uint8_t)(v >> 24); };
+    size_t w = 0, pos = data0;
+    for (uint32_t g = 0; g < nf; g++) {
+        offs[g] = w;
+        const uint8_t ftype = img[pos];
+        const uint32_t nsamp = rd32(pos + 1);
+        memcpy(buf + w, img + pos, 6);                       // frame_type, frame_samples, flags (encoder.rs:226-230)
+        w += 6; pos += 6;
+        for (uint32_t q = 0; q < ch; q++) {
+            const uint32_t size = rd32(pos);
+            const uint8_t *body = img + pos + 4;
+            pos += 4 + (size_t)size;
+            uint8_t *lenp = buf + w;
+            w += 4;
+            size_t cl = 0;
+            if (ftype == 254) {                              // Raw: at most 2 * frame_samples bytes (reader.rs:182-188)
+                cl = std::min<size_t>(2ull * nsamp, size);
+                memcpy(buf + w, body, cl);
+            } else if (ftype >= 1 && ftype <= 12 && size >= 3) {   // ALPC: k, coefficients, residual bytes
+                const uint32_t order = body[0];
+                size_t p = 1 + 4ull * order;
+                const uint8_t enc = body[p + 1];
+                const uint8_t k = enc == 0 ? body[p + 2] : 0;
+                p += enc == 0 ? 3 : 2;
+                buf[w] = k;
+                memcpy(buf + w + 1, body + 1, 4ull * order);
+                memcpy(buf + w + 1 + 4ull * order, body + p, size - p);
+                cl = 1 + 4ull * order + (size - p);
+            }                                                // Silence and anything else: an empty channel
+            wr32(lenp, (uint32_t)cl);
+            w += cl;
+        }
+    }
+    offs[nf] = w;
+    flo_free(img);
+    *out = buf; *out_len = w; *frame_off = offs; *n_frames = nf;
+    return FLO_OK;
 }
 
 // ------------------------------------------------------------------------------------------------

@@ -73,6 +73,8 @@ struct EncodeParams {
     uint32_t *counters;               // [0] loud frames, [1] pass-3 rounds, [2] LPC sizes from the window, [3] window misses,
                                       // [4] fixed candidates evaluated exactly, [5] candidates pruned by bounds
     uint32_t smem_plane_bytes;        // bytes of dynamic shared memory available for sample planes
+    const uint32_t *crc_tab;          // CRC tables in global memory (crc_tables_host layout), staged into shared memory by every CTA
+    uint32_t *frame_crc;              // out: raw CRC state R(frame bytes) of every frame (folded per track by k_crc_frames)
     uint32_t stagger;                 // SM clocks the second half of the CTAs waits before its first frame (de-phases the CTAs that share an SM)
     uint32_t work_bytes;              // bytes of the CTA's work area in shared memory (ingest stages / packer ring), multiple of 128, >= 16 KB
     unsigned long long *phase_cycles; // [0] ingest, [1] analysis, [2] look-back, [3] pack, [4] whole frame (SM clocks, thread 0)
@@ -88,7 +90,8 @@ struct FinalParams {
     const uint8_t *meta;              // metadata arena
     const unsigned long long *frame_excl;
     const uint32_t *frame_size;
-    uint32_t *track_crc;              // per track, zeroed; CRC segments XOR their shifted CRCs in
+    uint32_t *track_crc;              // per track, zeroed; the frames' shifted CRCs are XORed in
+    const uint32_t *frame_crc;        // raw CRC state of every frame's bytes (written by the encode kernel)
     uint32_t n_segs;
     unsigned long long *file_off;     // out: per track
     unsigned long long *file_len;     // out: per track
@@ -106,7 +109,11 @@ struct EncodeVariant {
 const EncodeVariant &encode_variant(int threads);     // 512, 256 or 128
 cudaError_t launch_setup(const TrackDev *tracks, uint32_t n_tracks, uint2 *frames, uint32_t n_frames, cudaStream_t st);
 cudaError_t launch_toc(const FinalParams &p, cudaStream_t st);
-cudaError_t launch_crc_segments(const FinalParams &p, cudaStream_t st);
+cudaError_t launch_crc_frames(const FinalParams &p, cudaStream_t st);
+// host copy of the CRC tables the encode kernel wants: slice0[256] | per NT in {128, 256, 512}: xop[4][256], klane[NT]
+constexpr int CRC_TAB_WORDS = 256 + 3 * 1024 + 128 + 256 + 512;
+__host__ __device__ constexpr int crc_tab_offset(int nt) { return 256 + (nt == 128 ? 0 : nt == 256 ? 1024 + 128 : 2 * 1024 + 128 + 256); }
+void crc_tables_host(uint32_t *out);
 cudaError_t launch_headers(const FinalParams &p, cudaStream_t st);
 void upload_crc_tables();
 // reflo's U8 / S32 ingest arms (reflo/src/audio.rs:255-269) as a pre-pass: interleaved PCM -> interleaved f32

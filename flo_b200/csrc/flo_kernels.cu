@@ -21,6 +21,7 @@
 // (one RN multiply) and the sequential f64 Levinson-Durbin recursion, both with
 // explicit _rn intrinsics so that no FMA contraction can change a bit.
 #include <cstdio>
+#include <cstring>
 #include <type_traits>
 
 #include "flo_internal.h"
@@ -56,6 +57,9 @@ static u32 h_x2nmodp(u64 n, unsigned k) {
     return p;
 }
 
+static u32 h_tab[CRC_TAB_WORDS];
+void crc_tables_host(uint32_t *out) { upload_crc_tables(); memcpy(out, h_tab, sizeof h_tab); }
+
 void upload_crc_tables() {
     static u32 slice[4][256];
     for (u32 i = 0; i < 256; i++) {
@@ -74,6 +78,16 @@ void upload_crc_tables() {
         for (u32 t = 0; t < 256; t++) xop[b][t] = h_multmodp(x1024, t << (8 * b));
     u32 klane[32];
     for (int l = 0; l < 32; l++) klane[l] = h_x2nmodp(4 * (32 - l), 3);
+    // tables of the encode kernel's per-frame CRC (one stream per thread of the CTA, see encode_v3_body.cuh):
+    // slice0[256] | for NT in 128, 256, 512: xop_NT[4][256] (v -> v * x^(32 NT)), klane_NT[NT] (x^(32 (NT - t)))
+    memcpy(h_tab, slice[0], 1024);
+    u32 *w = h_tab + 256;
+    for (int nt = 128; nt <= 512; nt *= 2) {
+        const u32 xs = h_x2nmodp((u64)4 * nt, 3);
+        for (int b = 0; b < 4; b++)
+            for (u32 t = 0; t < 256; t++) *w++ = h_multmodp(xs, t << (8 * b));
+        for (int t = 0; t < nt; t++) *w++ = h_x2nmodp((u64)4 * (nt - t), 3);
+    }
     cudaMemcpyToSymbol(c_crc_slice, slice, sizeof slice);
     cudaMemcpyToSymbol(c_x2n, h_x2n, sizeof h_x2n);
     cudaMemcpyToSymbol(c_xop, xop, sizeof xop);
@@ -138,65 +152,20 @@ __global__ void k_write_toc(const FinalParams p) {
     put_u32le(e + 16, (u32)ts);
 }
 
-// CRC-32 (crc32.rs:2-30) of a track's DATA chunk, one warp per 64 KB segment.
-//
-// Works on the raw CRC R(M) = M(x) x^32 mod p (zero initial state, no final complement), which is
-// linear: R(A || B) = R(A) x^(8|B|) ^ R(B), and leading zero bytes are free.  The reference's value is
-// crc(M) = ~(R(M) ^ 0xFFFFFFFF x^(8|M|)) (k_write_headers).  Inside a segment lane l takes the
-// aligned words l, l+32, l+64, ... (coalesced loads) counted so that the last word falls on lane 31,
-// and runs the Horner step d = d x^1024 ^ w -- four table look-ups, like an ordinary slice-by-4 step.
-// Lane l's stream then weighs x^(32 (32 - l)); the XOR over the lanes is the state after the last
-// whole word, and the <= 3 bytes behind it are added with the byte-wise step.  The segment's R is
-// shifted by the bytes that follow it in the track and XORed into the track's accumulator.
-__global__ void __launch_bounds__(CRC_NT) k_crc_segments(const FinalParams p) {
-    __shared__ u32 X[4][256];
-    for (int i = threadIdx.x; i < 1024; i += CRC_NT) (&X[0][0])[i] = (&c_xop[0][0])[i];
-    __syncthreads();
-    const u32 lane = threadIdx.x & 31;
-    const u32 seg = (blockIdx.x * CRC_NT + threadIdx.x) >> 5;
-    if (seg >= p.n_segs) return;
-    u32 lo = 0, hi = p.n_tracks;
-    while (hi - lo > 1) {
-        const u32 mid = (lo + hi) >> 1;
-        if (p.tracks[mid].first_seg <= seg) lo = mid; else hi = mid;
-    }
-    const TrackDev tr = p.tracks[lo];
-    const u64 e0 = excl_at(p, tr.first_frame), e1 = excl_at(p, tr.first_frame + tr.n_frames);
-    const u64 dsize = e1 - e0;
-    const u64 soff = (u64)(seg - tr.first_seg) * CRC_SEG;
-    if (soff >= dsize) return;
-    const u64 d0 = tr.static_off + e0 + FILE_HDR + 4 + 20ull * tr.n_frames;
-    const u64 a = d0 + soff;                                 // byte range [a, b) of p.out (p.out is 16-byte aligned)
-    const u64 b = a + min((u64)CRC_SEG, dsize - soff);
-    const u64 b4 = b & ~3ull;
-    u32 c = 0;
-    u64 tail = a;
-    if (b4 > a) {
-        const u64 a4 = a & ~3ull;
-        const u64 nwords = (b4 - a4) >> 2;
-        const u64 J = (nwords + 31) >> 5;
-        const i64 s0 = (i64)b4 - (i64)(128 * J);             // may lie before a4: those words count as zero
-        const u32 head_mask = 0xFFFFFFFFu << (8 * (u32)(a - a4));
-        u32 d = 0;
-        i64 addr = s0 + 4 * (i64)lane;
-        for (u64 j = 0; j < J; j++, addr += 128) {
-            u32 w = 0;
-            if (addr >= (i64)a4) {
-                w = __ldg(reinterpret_cast<const u32 *>(p.out + addr));
-                if (addr == (i64)a4) w &= head_mask;
-            }
-            d = X[0][d & 0xff] ^ X[1][(d >> 8) & 0xff] ^ X[2][(d >> 16) & 0xff] ^ X[3][d >> 24] ^ w;
-        }
-        c = multmodp(c_klane[lane], d);
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) c ^= __shfl_xor_sync(0xffffffffu, c, o);
-        tail = b4;
-    }
-    if (lane == 0) {
-        for (u64 i = tail; i < b; i++) c = (c >> 8) ^ c_crc_slice[0][(c ^ p.out[i]) & 0xff];
-        const u64 after = (d0 + dsize) - b;
-        atomicXor(&p.track_crc[lo], multmodp(x2nmodp(after, 3), c));
-    }
+// CRC32 of the DATA chunk (crc32.rs:23-30, writer.rs:58).  The raw CRC R(M) = M(x) x^32 mod p is linear and
+// ignores leading zeros, so the DATA chunk's CRC is the XOR of every frame's R shifted by the bytes that
+// follow the frame in the chunk.  The encode kernel leaves R(frame) in frame_crc (computed from the frame's bytes
+// while they are still in L2); this kernel only applies the shifts: one thread per frame.
+// multmodp / x2nmodp above follow zlib's crc32_combine helpers (zlib 1.2.12+, crc32.c; (C) 1995-2022 Mark Adler,
+// zlib licence), re-typed here.
+__global__ void k_crc_frames(const FinalParams p) {
+    const u32 g = blockIdx.x * blockDim.x + threadIdx.x;
+    if (g >= p.n_frames) return;
+    const uint2 fd = p.frames[g];
+    const TrackDev tr = p.tracks[fd.x];
+    const u64 e1 = excl_at(p, tr.first_frame + tr.n_frames);
+    const u64 after = e1 - (p.frame_excl[g] + p.frame_size[g]);
+    atomicXor(&p.track_crc[fd.x], multmodp(x2nmodp(after, 3), p.frame_crc[g]));
 }
 
 // write_header_ex, writer.rs:132-191, + metadata (writer.rs:96): one block per track
@@ -248,10 +217,9 @@ cudaError_t launch_toc(const FinalParams &p, cudaStream_t st) {
     k_write_toc<<<(p.n_frames + 255) / 256, 256, 0, st>>>(p);
     return cudaGetLastError();
 }
-cudaError_t launch_crc_segments(const FinalParams &p, cudaStream_t st) {
-    if (p.n_segs == 0) return cudaSuccess;
-    const uint32_t warps_per_block = CRC_NT / 32;
-    k_crc_segments<<<(p.n_segs + warps_per_block - 1) / warps_per_block, CRC_NT, 0, st>>>(p);
+cudaError_t launch_crc_frames(const FinalParams &p, cudaStream_t st) {
+    if (p.n_frames == 0) return cudaSuccess;
+    k_crc_frames<<<(p.n_frames + 127) / 128, 128, 0, st>>>(p);
     return cudaGetLastError();
 }
 cudaError_t launch_headers(const FinalParams &p, cudaStream_t st) {

@@ -102,25 +102,39 @@ class StreamingEncoder:
     def pending_frames(self) -> int:
         return len(self._pending)
 
-    def _encode_frames(self, frames: List[np.ndarray]) -> List[bytes]:
-        """encode_frame_data (encoder.rs:216-241) for several frames in one device pass."""
+    def _encode_run(self, samples: np.ndarray) -> List[bytes]:
+        """encode_frame_data (encoder.rs:216-241) for every frame of a contiguous run of samples: one device pass
+        and the re-serialisation in C (flo_stream_encode_frames, include/flo_b200.h)."""
         if self.channels == 0 or self.sample_rate == 0:
             raise FloError("channels and sample_rate must be non-zero")
-        tracks = [TrackSpec(f, self.sample_rate, self.channels, self.bit_depth, b"") for f in frames]
-        files = self._context().encode_batch(tracks, self.compression_level, FMT_F32)
-        return [reserialize_frame(f, self.channels) for f in files]
+        import ctypes as C
+        from . import _lib
+        ctx = self._context()
+        x = np.ascontiguousarray(samples, dtype=np.float32)
+        out, out_len, offs, nfr = C.c_void_p(), C.c_size_t(), C.c_void_p(), C.c_uint32()
+        _lib.check(ctx._L.flo_stream_encode_frames(ctx._h, x.ctypes.data_as(C.c_void_p), x.size, self.sample_rate, self.channels,
+                                                   self.bit_depth, self.compression_level, C.byref(out), C.byref(out_len),
+                                                   C.byref(offs), C.byref(nfr)))
+        try:
+            blob = C.string_at(out.value, out_len.value)
+            off = np.ctypeslib.as_array(C.cast(offs.value, C.POINTER(C.c_uint64)), shape=(nfr.value + 1,)).copy()
+        finally:
+            ctx._L.flo_free(out)
+            ctx._L.flo_free(offs)
+        return [blob[int(off[i]):int(off[i + 1])] for i in range(nfr.value)]
 
     def push_samples(self, samples) -> None:
         """encoder.rs:71-75 + try_encode_frames (encoder.rs:189-213)."""
-        self._buf = np.concatenate([self._buf, np.asarray(samples, dtype=np.float32).reshape(-1)])
+        x = np.asarray(samples, dtype=np.float32).reshape(-1)
+        self._buf = x if self._buf.size == 0 else np.concatenate([self._buf, x])     # (no copy for the common bulk push)
         frame_samples = self.samples_per_frame * self.channels
         if frame_samples == 0:
             raise FloError("channels and sample_rate must be non-zero")      # the reference loops forever / divides by zero
         nfull = self._buf.size // frame_samples
         if nfull == 0:
+            self._buf = self._buf.copy() if self._buf is x else self._buf         # never keep a view of the caller's array
             return
-        frames = [self._buf[i * frame_samples:(i + 1) * frame_samples] for i in range(nfull)]
-        for data in self._encode_frames(frames):
+        for data in self._encode_run(self._buf[:nfull * frame_samples]):
             ts = _f64_as_u32(self._total_samples / float(self.sample_rate) * 1000.0)
             self._pending.append(EncodedFrame(self._frame_index, ts, data, self.samples_per_frame))
             self._total_samples += self.samples_per_frame
@@ -136,7 +150,10 @@ class StreamingEncoder:
             return None
         per = self._per_channel(self._buf.size)
         ts = _f64_as_u32(self._total_samples / float(self.sample_rate) * 1000.0)
-        data = self._encode_frames([self._buf])[0]
+        run = self._encode_run(self._buf)
+        if not run:
+            raise FloError("No frames encoded")                               # encoder.rs:222-224
+        data = run[0]
         fr = EncodedFrame(self._frame_index, ts, data, per)
         self._total_samples += per
         self._frame_index = (self._frame_index + 1) & 0xFFFFFFFF

@@ -65,6 +65,16 @@ int flo_encode_pcm16(flo_ctx *ctx, const int16_t *pcm, size_t n_interleaved,
                      uint32_t sample_rate, uint8_t channels, uint8_t bit_depth, uint8_t level,
                      const uint8_t *meta, size_t meta_len, uint8_t **out, size_t *out_len);
 
+/* StreamingEncoder::encode_frame_data (libflo/src/streaming/encoder.rs:216-257) for every frame of `samples`
+ * (whole 1-second frames and, if the length is not a multiple, one partial frame at the end): one device pass
+ * for the whole run, then the reference's per-frame layout -- frame_type, frame_samples u32, flags, and per
+ * channel a u32 length + [rice_parameter][coefficients as i32 LE][residual bytes] (serialize_channel, :243-257).
+ * *out holds the frames back to back, frame i = (*out)[(*frame_off)[i] .. (*frame_off)[i + 1]); *frame_off has
+ * *n_frames + 1 entries.  Both are malloc'd by the library: release each with flo_free. */
+int flo_stream_encode_frames(flo_ctx *ctx, const float *samples, size_t n_interleaved,
+                             uint32_t sample_rate, uint8_t channels, uint8_t bit_depth, uint8_t level,
+                             uint8_t **out, size_t *out_len, uint64_t **frame_off, uint32_t *n_frames);
+
 /* Batched entry (additive; the reference has no batch call -- it is a loop of
  * Encoder::encode over tracks, reflo/src/main.rs:218-276).  Frames of all
  * tracks are encoded in one device pass.  Every track gets exactly the bytes

@@ -66,6 +66,9 @@ extern "C" {
     pub fn flo_encode_batch_device(ctx: *mut flo_ctx, tracks: *const flo_track, n_tracks: usize, format: c_int,
                                    level: u8, d_out: *mut c_void, d_out_capacity: usize,
                                    offsets: *mut u64, lens: *mut u64) -> c_int;
+    pub fn flo_stream_encode_frames(ctx: *mut flo_ctx, samples: *const f32, n_interleaved: usize, sample_rate: u32,
+                                    channels: u8, bit_depth: u8, level: u8, out: *mut *mut u8, out_len: *mut usize,
+                                    frame_off: *mut *mut u64, n_frames: *mut u32) -> c_int;
     pub fn flo_decode(ctx: *mut flo_ctx, file: *const u8, len: usize, out: *mut *mut f32, n_interleaved: *mut usize,
                       info: *mut flo_info) -> c_int;
     pub fn flo_decode_device(ctx: *mut flo_ctx, d_file: *const c_void, len: usize, d_out: *mut f32,

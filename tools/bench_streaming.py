@@ -32,3 +32,16 @@ n = enc2.pending_frames()
 out = enc2.finalize(b"")
 print(json.dumps({"per_frame_push_ms_median": float(np.median(lat)), "per_frame_push_ms_min": float(min(lat)),
                   "bulk_frames": n, "bulk_push_ms": dt * 1e3, "bulk_x_realtime": n / dt, "file_bytes": len(out)}))
+# where the bulk push spends its time: the C entry alone (one device pass + re-serialisation), then the Python mirror
+import ctypes as C
+from flo_b200 import _lib
+ctx = flo_b200.default_context(0)
+xc = np.ascontiguousarray(x)
+ts = []
+for _ in range(3):
+    out, out_len, offs, nfr = C.c_void_p(), C.c_size_t(), C.c_void_p(), C.c_uint32()
+    t0 = time.perf_counter()
+    _lib.check(ctx._L.flo_stream_encode_frames(ctx._h, xc.ctypes.data_as(C.c_void_p), xc.size, sr, ch, 16, 5, C.byref(out), C.byref(out_len), C.byref(offs), C.byref(nfr)))
+    ts.append((time.perf_counter() - t0) * 1e3)
+    ctx._L.flo_free(out); ctx._L.flo_free(offs)
+print(json.dumps({"flo_stream_encode_frames_ms_600_frames": min(ts), "frames": nfr.value, "bytes": out_len.value}))
