@@ -1851,12 +1851,16 @@ __global__ void __launch_bounds__(NT, FLO_VARIANT_CTAS) k_encode_frames(const En
         if (tid < 32) {
             u64 ex = lookback_exclusive(p.status, g, fsize);
             if (tid == 0) { s.frame_excl = ex; p.frame_excl[g] = ex; p.frame_size[g] = fsize; }
-        } else if (tid >= NT - 32) {
-            // while this frame is packed, ask for the input of the frame this CTA is likely to take next
-            // (tickets go round the resident CTAs in steady state): ingest then reads L2, not DRAM
+        }
+#ifdef FLO_PREFETCH_NEXT_FRAME
+        // Asking for the input of the frame this CTA is likely to take next (g + gridDim.x) while this one is packed
+        // was measured: no gain in kernel time, and 296 frames of input parked in L2 beside the planes push each
+        // other out -- DRAM reads rose from 1.0 x to 1.4 x the input bytes.  Off.
+        else if (tid >= NT - 32) {
             const u32 gn = g + gridDim.x;
             if (gn < p.frame_end) prefetch_frame_l2(p, gn);
         }
+#endif
         __syncthreads();
 
         PH(const long long tc3 = clock64();)
