@@ -22,6 +22,11 @@ constexpr int NWARP = NT / 32;
 #ifndef FLO_PAIR_BS
 #define FLO_PAIR_BS 4         // samples per block of the two-order FIR sweeps (independent chains = 2 x this)
 #endif
+#ifdef FLO_PASSES_NOINLINE    // experiment: the passes as real calls (their own register allocation)
+#define PASS_FN __device__ __noinline__
+#else
+#define PASS_FN __device__
+#endif
 #ifdef FLO_PHASE_CLOCKS
 #define PH(...) __VA_ARGS__
 #else
@@ -104,6 +109,9 @@ struct Smem {
     u64 partA[GROUP][NCAND][NWARP];   // sum|r| per region (fixed: pass 1, LPC: pass 2)
     u64 partT[GROUP][NLPC][2][NWARP]; // pass 2: sum(w >> j0), sum(w >> (j0 + 1)) per region
     u64 partS[GROUP][NCAND][NWARP];   // pass 3: exact sum(w >> j) per region
+    u64 partAC[GROUP][MAXORD + 1][NWARP];   // pass 1: autocorrelation lags per region
+    // (a region's slots are written by its own warp only -- plain read-modify-write, no 64-bit shared-memory
+    //  atomics, which are compare-and-swap loops; the channel totals are summed over the regions afterwards)
     u32 edge[GROUP][NWARP + 1];       // packer: bits of the words shared by two regions, by boundary
     i32 redo[GROUP];                  // a channel asks for the second run of pass 2
     // CRC32 of the frame's bytes (crc32.rs): tables staged from global memory once per CTA
@@ -548,7 +556,7 @@ __device__ __forceinline__ void for_chunks(const Smem &s, int nch, Reset &&reset
 
 // ---- pass 1: fixed-predictor statistics (sum|r|, OR|r|) for orders 0..NF-1 + autocorrelation (lpc.rs:213-221) ----
 template <int P, int NF>
-__device__ void pass1(Smem &s, int nch) {
+PASS_FN void pass1(Smem &s, int nch) {
     constexpr int NHF = NF > 1 ? 4 : 0;
     constexpr int NH = P > 8 ? 12 : (P > 0 ? 8 : NHF);
     u32 fsum[NF], forr[NF];             // |r| <= 2^20 for the fixed predictors: 2^24 per chunk
@@ -605,13 +613,13 @@ __device__ void pass1(Smem &s, int nch) {
             for (int o = 0; o < NF; o++) {
                 const u64 t = warp_sum64((u64)fsum[o]);
                 const u32 r = __reduce_or_sync(0xffffffffu, forr[o]);
-                if (lane == 0) { atomic_add64(&cs.fix_sum[o], t); atomicOr(&cs.fix_or[o], r); atomic_add64(&s.partA[c][1 + o][region], t); }
+                if (lane == 0) { atomicOr(&cs.fix_or[o], r); s.partA[c][1 + o][region] += t; }
             }
             if constexpr (P > 0) {
 #pragma unroll
                 for (int l = 0; l <= P; l++) {
                     const u64 t = warp_sum64((u64)__double2ll_rn(acc[l]));
-                    if (lane == 0) atomic_add64(reinterpret_cast<u64 *>(&cs.ac[l]), t);
+                    if (lane == 0) s.partAC[c][l][region] += t;
                 }
             }
         });
@@ -661,7 +669,7 @@ struct Sweeps {
 
 // orders LO..HI (at most four) in one pass over the channel
 template <int P, int LO, int HI>
-__device__ void pass2_range(Smem &s, int nch) {
+PASS_FN void pass2_range(Smem &s, int nch) {
     constexpr int NO = HI - LO + 1;
     constexpr int NH = P > 8 ? 12 : 8;
     // 32-bit partial sums: only candidates with OR|r| < 2^21 are ever used (after_pass2), 2^25 per chunk
@@ -695,10 +703,9 @@ __device__ void pass2_range(Smem &s, int nch) {
                 const u64 a = warp_sum64((u64)st[i].sum), b = warp_sum64((u64)st[i].t0), d = warp_sum64((u64)st[i].t1);
                 const u32 r = __reduce_or_sync(0xffffffffu, st[i].orr);
                 if (lane == 0) {
-                    atomic_add64(&cs.l_sum[LO - 5 + i], a); atomic_add64(&cs.l_t0[LO - 5 + i], b); atomic_add64(&cs.l_t1[LO - 5 + i], d);
                     atomicOr(&cs.l_or[LO - 5 + i], r);
-                    atomic_add64(&s.partA[c][6 + LO - 5 + i][region], a);
-                    atomic_add64(&s.partT[c][LO - 5 + i][0][region], b); atomic_add64(&s.partT[c][LO - 5 + i][1][region], d);
+                    s.partA[c][6 + LO - 5 + i][region] += a;
+                    s.partT[c][LO - 5 + i][0][region] += b; s.partT[c][LO - 5 + i][1][region] += d;
                 }
             }
         });
@@ -734,7 +741,7 @@ __device__ __forceinline__ void cand_chunk(const i32 (&x)[NHX + CH], const doubl
 
 // ---- pass 3: exact max|r| and S = sum(w >> j) for one still-open candidate per channel ----
 template <int P, int NF>
-__device__ void pass3(Smem &s, int nch) {
+PASS_FN void pass3(Smem &s, int nch) {
     constexpr int NH = P > 8 ? 12 : (P > 0 ? 8 : (NF > 1 ? 4 : 0));
     u64 S;
     u32 mx;
@@ -820,14 +827,14 @@ __device__ void pass3(Smem &s, int nch) {
             const u64 t = warp_sum64(S);
             const u32 m = __reduce_max_sync(0xffffffffu, mx);
             if (lane == 0 && cs.ex_cand >= 0) {
-                atomic_add64(&cs.ex_s, t); atomicMax(&cs.ex_max, m);
-                if (!cs.ex_fixed) atomic_add64(&s.partS[c][cs.ex_cand][region], t);
+                atomicMax(&cs.ex_max, m);
+                if (!cs.ex_fixed) s.partS[c][cs.ex_cand][region] += t;
             }
             if (cs.ex_fixed) {
 #pragma unroll
                 for (int o = 0; o < NF; o++) {
                     const u64 t5 = warp_sum64((u64)S5[o]);
-                    if (lane == 0 && (cs.ex_fixed >> o & 1)) { atomic_add64(&cs.ex_s5[o], t5); atomic_add64(&s.partS[c][1 + o][region], t5); }
+                    if (lane == 0 && (cs.ex_fixed >> o & 1)) s.partS[c][1 + o][region] += t5;
                 }
             }
         });
@@ -841,9 +848,14 @@ __device__ void pass3(Smem &s, int nch) {
 
 // after pass 1: k of every fixed candidate, raw size; then Levinson
 template <int P>
-__device__ void after_pass1_warp(ChanState &cs, int fmax, bool lpc_on) {
+__device__ void after_pass1_warp(Smem &s, int c, int fmax, bool lpc_on) {
+    ChanState &cs = s.cs[c];
     const int lane = threadIdx.x & 31;
     const u32 n = (u32)cs.n;
+    // channel totals = sums over the regions
+    if (lane < 5) { u64 t = 0; for (int w = 0; w < NWARP; w++) t += s.partA[c][1 + lane][w]; cs.fix_sum[lane] = t; }
+    if (lane <= P) { u64 t = 0; for (int w = 0; w < NWARP; w++) t += s.partAC[c][lane][w]; cs.ac[lane] = (i64)t; }
+    __syncwarp();
     if (lane < NCAND) {
         int state = CS_ABSENT, k = 0;
         i64 size = -1;
@@ -881,6 +893,9 @@ __device__ bool after_pass2_warp(Smem &s, int c, int P, bool redo, u32 *counters
     int k = 0;
     if (mine) {
         const int i = o - 5;
+        u64 ta = 0, t0 = 0, t1 = 0;                                               // channel totals = sums over the regions
+        for (int w = 0; w < NWARP; w++) { ta += s.partA[c][lane][w]; t0 += s.partT[c][i][0][w]; t1 += s.partT[c][i][1][w]; }
+        cs.l_sum[i] = ta; cs.l_t0[i] = t0; cs.l_t1[i] = t1;
         const u32 orr = cs.l_or[i];
         const int bl = bitlen32(orr);
         if (bl < 21) {                                                            // else max|r| >= 2^20 > 1_000_000: rejected
@@ -964,18 +979,23 @@ __device__ int next_open_candidate_warp(ChanState &cs, bool prune, u32 *counters
     return pick;
 }
 
-__device__ void after_pass3(ChanState &cs) {
+__device__ void after_pass3(Smem &s, int ch) {
+    ChanState &cs = s.cs[ch];
     const int c = cs.ex_cand;
     if (c < 0) return;
     const u32 n = (u32)cs.n;
     if (cs.ex_fixed) {
         for (int o = 0; o < 5; o++)
             if (cs.ex_fixed >> o & 1) {
+                u64 t = 0;
+                for (int w = 0; w < NWARP; w++) t += s.partS[ch][1 + o][w];
+                cs.ex_s5[o] = t;
                 cs.cand_state[1 + o] = CS_EXACT;
                 cs.cand_size[1 + o] = rice_bytes(cs.ex_s5[o], cs.cand_sumabs[1 + o], n, cs.cand_k[1 + o]);
             }
         return;
     }
+    { u64 t = 0; for (int w = 0; w < NWARP; w++) t += s.partS[ch][c][w]; cs.ex_s = t; }
     if (c >= 6 && cs.ex_max > 1000000u) { cs.cand_state[c] = CS_ABSENT; return; }   // encoder.rs:269-272
     cs.cand_state[c] = CS_EXACT;
     cs.cand_size[c] = rice_bytes(cs.ex_s, cs.cand_sumabs[c], n, cs.cand_k[c]);
@@ -1158,7 +1178,7 @@ __device__ __forceinline__ u32 region_samples(int n, int W, int wi) {
 // 162-208) or encode_raw (encoder.rs:220-226).  The region's bit offset inside the payload is the sum of the
 // bit counts of the regions in front (cr.regbits, from the analysis passes); no block-wide step is needed.
 template <int P>
-__device__ void pack_region(Smem &s, u32 *ring, const ChanState &cs, int cq, const ChanResult &cr, uint8_t *obase, u64 pos, int wi, int W,
+PASS_FN void pack_region(Smem &s, u32 *ring, const ChanState &cs, int cq, const ChanResult &cr, uint8_t *obase, u64 pos, int wi, int W,
                             u32 *err) {
     const int lane = threadIdx.x & 31;
     const int n = cs.n, nfull = n / CH, tail = n % CH;
@@ -1695,6 +1715,7 @@ __global__ void __launch_bounds__(NT, FLO_VARIANT_CTAS) k_encode_frames(const En
             __syncthreads();
             for (int i = tid; i < GROUP * NCAND * NWARP; i += NT) { (&s.partA[0][0][0])[i] = 0; (&s.partS[0][0][0])[i] = 0; }
             for (int i = tid; i < GROUP * NLPC * 2 * NWARP; i += NT) (&s.partT[0][0][0][0])[i] = 0;
+            for (int i = tid; i < GROUP * (MAXORD + 1) * NWARP; i += NT) (&s.partAC[0][0][0])[i] = 0;
             if (tid < nch) {
                 ChanState &cs = s.cs[tid];
                 const u32 c = c0 + tid;
@@ -1726,7 +1747,7 @@ __global__ void __launch_bounds__(NT, FLO_VARIANT_CTAS) k_encode_frames(const En
             else pass1<0, 1>(s, nch);
             __syncthreads();
             PH(const long long ta1 = clock64();)
-            if ((tid >> 5) < nch && s.cs[tid >> 5].n > 0) after_pass1_warp<P>(s.cs[tid >> 5], fmax, lpc_on);
+            if ((tid >> 5) < nch && s.cs[tid >> 5].n > 0) after_pass1_warp<P>(s, tid >> 5, fmax, lpc_on);
             LV(if (tid == 0) atomicAdd(p.phase_cycles + 14, (u64)(clock64() - ta1)); if (tid == 32) atomicAdd(p.phase_cycles + 12, (u64)(clock64() - ta1));)
             __syncthreads();
             PH(const long long ta2 = clock64();)
@@ -1771,7 +1792,7 @@ __global__ void __launch_bounds__(NT, FLO_VARIANT_CTAS) k_encode_frames(const En
                 __syncthreads();
                 if ((tid >> 5) < nch && s.cs[tid >> 5].n > 0) {
                     ChanState &cs = s.cs[tid >> 5];
-                    if ((tid & 31) == 0) after_pass3(cs);
+                    if ((tid & 31) == 0) after_pass3(s, tid >> 5);
                     __syncwarp();
                     next_open_candidate_warp(cs, prune, s.cnt);
                 }
