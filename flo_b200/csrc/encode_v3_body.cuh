@@ -114,6 +114,7 @@ struct Smem {
     //  atomics, which are compare-and-swap loops; the channel totals are summed over the regions afterwards)
     u32 edge[GROUP][NWARP + 1];       // packer: bits of the words shared by two regions, by boundary
     i32 redo[GROUP];                  // a channel asks for the second run of pass 2
+    ChanResult wres[GROUP];           // the winners of the channels being packed (copied from global memory once)
     // CRC32 of the frame's bytes (crc32.rs): tables staged from global memory once per CTA
     u32 crc_x[4][256];                // v -> v * x^(32 NT) mod p, by byte of v (the strided Horner step)
     u32 crc_klane[NT];                // x^(32 (NT - t)) mod p
@@ -1320,14 +1321,15 @@ __device__ __forceinline__ void st_status(u64 *p, u64 v) {
     asm volatile("st.relaxed.gpu.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
 }
 
-// called by warp 0; returns the exclusive prefix in every lane
-__device__ u64 lookback_exclusive(u64 *status, u32 g, u64 mine) {
+// Two halves, both called by warp 0: publish makes this frame's size visible to its successors, wait returns
+// the exclusive prefix in every lane and publishes the inclusive one.  Whatever the CTA does between the two
+// (packing a small frame into its scratch) is time its predecessors have to publish in.
+__device__ __forceinline__ void lookback_publish(u64 *status, u32 g, u64 mine) {
+    if ((threadIdx.x & 31) == 0) st_status(status + g, (g == 0 ? ST_PRE : ST_AGG) | mine);
+}
+__device__ u64 lookback_wait(u64 *status, u32 g, u64 mine) {
     const int lane = threadIdx.x & 31;
-    if (g == 0) {
-        if (lane == 0) st_status(status, ST_PRE | mine);
-        return 0;
-    }
-    if (lane == 0) st_status(status + g, ST_AGG | mine);
+    if (g == 0) return 0;
     u64 excl = 0;
     i64 idx = (i64)g - 1;
     for (;;) {
@@ -1351,6 +1353,31 @@ __device__ u64 lookback_exclusive(u64 *status, u32 g, u64 mine) {
     }
     if (lane == 0) st_status(status + g, ST_PRE | (excl + mine));
     return excl;
+}
+__device__ __forceinline__ u64 lookback_exclusive(u64 *status, u32 g, u64 mine) {
+    lookback_publish(status, g, mine);
+    return lookback_wait(status, g, mine);
+}
+
+// A frame packed into the CTA's scratch (16-byte aligned, frame-relative) goes to its place in the output, which
+// may start at any byte: whole 16-byte units of the destination are assembled from five aligned source words,
+// the <= 15 bytes in front of and behind them are stored byte-wise (the neighbours belong to other CTAs).
+__device__ __forceinline__ void copy_frame_out(const uint8_t *src, uint8_t *dst, u32 n) {
+    const u32 tid = threadIdx.x;
+    const u32 head = min(n, (u32)((16u - (u32)((uintptr_t)dst & 15u)) & 15u));
+    if (tid < head) dst[tid] = __ldcg(src + tid);
+    const u32 units = (n - head) >> 4;
+    const u32 sb = 8u * (head & 3u);
+    const u32 *s32 = reinterpret_cast<const u32 *>(src) + (head >> 2);
+    uint4 *d16 = reinterpret_cast<uint4 *>(dst + head);
+#pragma unroll 4
+    for (u32 u = tid; u < units; u += NT) {
+        const u32 *q = s32 + 4 * u;
+        const u32 w0 = __ldcg(q), w1 = __ldcg(q + 1), w2 = __ldcg(q + 2), w3 = __ldcg(q + 3), w4 = sb ? __ldcg(q + 4) : 0u;
+        d16[u] = make_uint4(__funnelshift_r(w0, w1, sb), __funnelshift_r(w1, w2, sb), __funnelshift_r(w2, w3, sb), __funnelshift_r(w3, w4, sb));
+    }
+    const u32 done = head + 16u * units;
+    if (tid < n - done) dst[done + tid] = __ldcg(src + done + tid);
 }
 
 // ----------------------------------------------------------------------------
@@ -1560,10 +1587,9 @@ __device__ __forceinline__ u32 crc_multmodp(u32 a, u32 b) {
     }
     return p;
 }
-// raw CRC of the bytes [a, a + fsize) of p.out -> p.frame_crc[g]; the bytes must be visible (barrier before)
-__device__ __noinline__ void crc_frame(Smem &s, const EncodeParams &p, u32 g, u64 a, u32 fsize) {
+// raw CRC of the bytes [a, a + fsize) of out -> p.frame_crc[g]; the bytes must be visible (barrier before)
+__device__ __noinline__ void crc_frame(Smem &s, const EncodeParams &p, const uint8_t *out, u32 g, u64 a, u32 fsize) {
     const int tid = threadIdx.x;
-    const uint8_t *out = p.out;
     const u64 b = a + fsize, b4 = b & ~3ull;
     if (b4 > a) {
         const u64 a4 = a & ~3ull;
@@ -1600,6 +1626,7 @@ __device__ __noinline__ void crc_frame(Smem &s, const EncodeParams &p, u32 g, u6
     }
 }
 
+static_assert(sizeof(ChanResult) % 4 == 0, "ChanResult is copied word by word");
 // ----------------------------------------------------------------------------
 // the frame-encode kernel
 // ----------------------------------------------------------------------------
@@ -1687,7 +1714,7 @@ __global__ void __launch_bounds__(NT, FLO_VARIANT_CTAS) k_encode_frames(const En
             if (tid == 0) { o[0] = 0; put_u32le(o + 1, frame_samples); o[5] = 0; }
             for (u32 i = tid; i < 4 * C; i += NT) o[6 + i] = 0;
             __syncthreads();
-            crc_frame(s, p, g, data_base + s.frame_excl, fsize);
+            crc_frame(s, p, p.out, g, data_base + s.frame_excl, fsize);
             if (p.report) {
                 for (u32 i = tid; i < REPORT_CH * NCAND; i += NT) {
                     flo_cand_report *r = p.report + (size_t)g * REPORT_CH * NCAND + i;
@@ -1869,9 +1896,17 @@ __global__ void __launch_bounds__(NT, FLO_VARIANT_CTAS) k_encode_frames(const En
             const ChanResult &r = cres[c];
             fsize += 4 + chan_hdr_bytes(all_raw, r) + r.nbytes;
         }
+        // A frame that fits the CTA's scratch is packed there, frame-relative, and copied to its place afterwards:
+        // its offset is then only asked for after the pack, when the frames in front of it have long published
+        // their sizes.  With 592 CTAs of short frames in flight the wait in front of the pack was 30 % of the
+        // frame's time (every CTA waits for the slowest analysis among its predecessors, then all move on together).
+        const bool defer = p.defer_bytes != 0 && fsize + 64u <= p.defer_bytes;
         if (tid < 32) {
-            u64 ex = lookback_exclusive(p.status, g, fsize);
-            if (tid == 0) { s.frame_excl = ex; p.frame_excl[g] = ex; p.frame_size[g] = fsize; }
+            lookback_publish(p.status, g, fsize);
+            if (!defer) {
+                u64 ex = lookback_wait(p.status, g, fsize);
+                if (tid == 0) { s.frame_excl = ex; p.frame_excl[g] = ex; p.frame_size[g] = fsize; }
+            }
         }
 #ifdef FLO_PREFETCH_NEXT_FRAME
         // Asking for the input of the frame this CTA is likely to take next (g + gridDim.x) while this one is packed
@@ -1886,8 +1921,8 @@ __global__ void __launch_bounds__(NT, FLO_VARIANT_CTAS) k_encode_frames(const En
 
         PH(const long long tc3 = clock64();)
         // write the frame, writer.rs:236-301
-        const u64 fpos = data_base + s.frame_excl;
-        uint8_t *o = p.out;
+        const u64 fpos = defer ? 0ull : data_base + s.frame_excl;
+        uint8_t *o = defer ? p.defer_scratch + (size_t)blockIdx.x * p.defer_bytes : p.out;
         if (tid == 0) {
             o[fpos] = (uint8_t)(all_raw ? 254u : frame_type_alpc);
             put_u32le(o + fpos + 1, frame_samples);
@@ -1904,13 +1939,12 @@ __global__ void __launch_bounds__(NT, FLO_VARIANT_CTAS) k_encode_frames(const En
             const int W = nchp == 2 ? NWARP / 2 : NWARP;
             u64 cpos[GROUP];
             u32 chdr[GROUP];
-            for (int q = 0; q < nchp; q++) {
-                const ChanResult &r = cres[c0 + q];
-                chdr[q] = chan_hdr_bytes(all_raw, r);
-                cpos[q] = pos;
-                pos += 4 + chdr[q] + r.nbytes;
-            }
             __syncthreads();
+            {   // the winners of this group: global -> shared, once (every later read is a shared-memory read)
+                constexpr int WORDS = (int)(sizeof(ChanResult) / 4);
+                for (int i = tid; i < nchp * WORDS; i += NT)
+                    reinterpret_cast<u32 *>(&s.wres[i / WORDS])[i % WORDS] = reinterpret_cast<const u32 *>(&cres[c0 + i / WORDS])[i % WORDS];
+            }
             if (tid < nchp) {
                 ChanState &cs = s.cs[tid];
                 const u32 c = c0 + tid;
@@ -1924,13 +1958,20 @@ __global__ void __launch_bounds__(NT, FLO_VARIANT_CTAS) k_encode_frames(const En
                 cs.pb = planes + stride;
                 cs.glob = planes != smem_planes;
             }
-            if (tid < nchp * MAXORD) {
-                const ChanResult &r = cres[c0 + tid / MAXORD];
-                s.wqd[tid / MAXORD][tid % MAXORD] = ldexp((double)r.coef[tid % MAXORD], -r.shift);
-            }
             for (int i = tid; i < GROUP * (NWARP + 1); i += NT) (&s.edge[0][0])[i] = 0;
             __syncthreads();
-            const ChanResult &r = cres[c0 + cq];
+            for (int q = 0; q < nchp; q++) {
+                const ChanResult &rq = s.wres[q];
+                chdr[q] = chan_hdr_bytes(all_raw, rq);
+                cpos[q] = pos;
+                pos += 4 + chdr[q] + rq.nbytes;
+            }
+            if (tid < nchp * MAXORD) {
+                const ChanResult &rq = s.wres[tid / MAXORD];
+                s.wqd[tid / MAXORD][tid % MAXORD] = ldexp((double)rq.coef[tid % MAXORD], -rq.shift);
+            }
+            __syncthreads();
+            const ChanResult &r = s.wres[cq];
             if (wi == 0 && (tid & 31) == 0) {
                 const u64 cp = cpos[cq];
                 put_u32le(o + cp, chdr[cq] + r.nbytes);
@@ -1971,7 +2012,17 @@ __global__ void __launch_bounds__(NT, FLO_VARIANT_CTAS) k_encode_frames(const En
         }
         if (tid == 0 && pos - fpos != fsize) atomicExch(p.err, 0xBAD00002u);
         __syncthreads();
-        crc_frame(s, p, g, fpos, fsize);
+        crc_frame(s, p, o, g, fpos, fsize);
+        PH(const long long tc3b = clock64();)
+        if (defer) {
+            if (tid < 32) {
+                u64 ex = lookback_wait(p.status, g, fsize);
+                if (tid == 0) { s.frame_excl = ex; p.frame_excl[g] = ex; p.frame_size[g] = fsize; }
+            }
+            __syncthreads();
+            PH(if (tid == 0) atomicAdd(p.phase_cycles + 15, (u64)(clock64() - tc3b));)
+            copy_frame_out(o, p.out + data_base + s.frame_excl, fsize);
+        }
         PH(if (tid == 0) {
             const long long tc4 = clock64();
             atomicAdd(p.phase_cycles + 0, (u64)(tc1 - tc0)); atomicAdd(p.phase_cycles + 1, (u64)(tc2 - tc1));

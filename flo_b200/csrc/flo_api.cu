@@ -240,6 +240,7 @@ struct flo_ctx {
     DevBuf in, out, meta, tracks, frames, ctrl, fexcl, fsize, foff, plane, cres, report;
     DevBuf dec_frames, dec_units, dec_base, dec_ctl;      // decoder scratch
     DevBuf conv;                                           // f32 samples of the U8 / S32 ingest pre-pass
+    DevBuf defer;                                          // per-CTA scratch of frames packed before their offset is known
     DevBuf crc_tab, fcrc;                                  // CRC tables for the encode kernel; raw CRC of every frame
     uint64_t counters[24] = {0};      // [0..7] analysis counters, [8..23] per-phase SM clock sums
     HostBuf h_small, h_out;
@@ -331,7 +332,7 @@ extern "C" void flo_ctx_destroy(flo_ctx *c) {
     }
     if (c->persist_prev != (size_t)-1) { cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, c->persist_prev); cudaGetLastError(); }
     for (DevBuf *b : {&c->in, &c->out, &c->meta, &c->tracks, &c->frames, &c->ctrl, &c->fexcl, &c->fsize,
-                      &c->foff, &c->plane, &c->cres, &c->report, &c->crc_tab, &c->fcrc, &c->dec_frames, &c->dec_units, &c->dec_base, &c->dec_ctl, &c->conv})
+                      &c->foff, &c->plane, &c->cres, &c->report, &c->crc_tab, &c->fcrc, &c->defer, &c->dec_frames, &c->dec_units, &c->dec_base, &c->dec_ctl, &c->conv})
         b->release();
     c->h_small.release();
     c->h_out.release();
@@ -586,6 +587,12 @@ static int encode_batch_impl(flo_ctx *c, const flo_track *tracks, size_t n_track
     int grid = (int)std::min<uint64_t>(std::max<uint64_t>(NF, 1), (uint64_t)c->sm_count * ctas_per_sm);
     if (const char *e = getenv("FLO_B200_GRID")) grid = std::max(1, std::min(grid, atoi(e)));   // experiments
     if ((rc = c->cres.reserve(sizeof(ChanResult) * 256ull * grid))) return rc;
+    // Frames of up to ~48 KB are packed into a per-CTA scratch (L2-resident: at most 592 x 48 KB) and copied to
+    // their place once the offset is known; larger frames wait for their offset and are packed in place.
+    // FLO_B200_DEFER_KB overrides the limit (0: every frame is packed in place).
+    size_t defer_bytes = 48u << 10;
+    if (const char *e = getenv("FLO_B200_DEFER_KB")) defer_bytes = (size_t)std::max(0, atoi(e)) << 10;
+    if (defer_bytes && (rc = c->defer.reserve(defer_bytes * (size_t)grid))) return rc;
     uint64_t plane_elems = 0;
     if (L.max_plane_elems * 2 > plane_cap) {
         plane_elems = align_up(L.max_plane_elems, 64);
@@ -671,6 +678,8 @@ static int encode_batch_impl(flo_ctx *c, const flo_track *tracks, size_t n_track
     ep.report = c->report_on ? (flo_cand_report *)c->report.p : nullptr;
     ep.smem_plane_bytes = (uint32_t)plane_cap;
     ep.work_bytes = (uint32_t)work;
+    ep.defer_bytes = (uint32_t)defer_bytes;
+    ep.defer_scratch = (uint8_t *)c->defer.p;
     ep.crc_tab = (const uint32_t *)c->crc_tab.p;
     ep.frame_crc = (uint32_t *)c->fcrc.p;
     ep.stagger = getenv("FLO_B200_STAGGER") ? (uint32_t)atoi(getenv("FLO_B200_STAGGER")) : 0u;

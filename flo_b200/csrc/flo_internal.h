@@ -77,6 +77,8 @@ struct EncodeParams {
     uint32_t *frame_crc;              // out: raw CRC state R(frame bytes) of every frame (folded per track by k_crc_frames)
     uint32_t stagger;                 // SM clocks the second half of the CTAs waits before its first frame (de-phases the CTAs that share an SM)
     uint32_t work_bytes;              // bytes of the CTA's work area in shared memory (ingest stages / packer ring), multiple of 128, >= 16 KB
+    uint32_t defer_bytes;             // per-CTA stride of defer_scratch; a frame of fsize + 64 <= defer_bytes is packed there first (0: never)
+    uint8_t *defer_scratch;           // grid x defer_bytes: frames packed before their output offset is known (small frames, see k_encode_frames)
     unsigned long long *phase_cycles; // [0] ingest, [1] analysis, [2] look-back, [3] pack, [4] whole frame (SM clocks, thread 0)
 };
 

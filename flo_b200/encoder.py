@@ -69,7 +69,7 @@ class Context:
         keys = ["loud_frames", "exact_rounds", "lpc_window_hits", "lpc_window_misses", "fixed_exact", "pruned"]
         d = {k: int(v) for k, v in zip(keys, buf)}
         d["phase_clocks"] = {k: int(buf[8 + i]) for i, k in enumerate(["ingest", "analysis", "lookback", "pack", "frame", "pack_codes", "pack_scan", "pack_emit",
-                                                                 "pass1", "levinson", "pass2", "exact_select", "ingest_desc", "ingest_thread0", "pack_flush_thread0"])}
+                                                                 "pass1", "levinson", "pass2", "exact_select", "ingest_desc", "ingest_thread0", "pack_flush_thread0", "deferred_wait"])}
         return d
 
     # -- encode entries ----------------------------------------------------------------
