@@ -42,6 +42,7 @@ EXPORTS = [
     "flo_encode_batch_device", "flo_output_bound", "flo_ctx_set_stream", "flo_ctx_last_timing",
     "flo_ctx_last_counters", "flo_ctx_enable_report", "flo_ctx_read_report", "flo_host_alloc", "flo_host_free", "flo_free",
     "flo_last_error", "flo_version", "flo_device_count", "flo_decode", "flo_decode_device", "flo_stream_encode_frames",
+    "flo_waveform_peaks", "flo_waveform_peaks_device", "flo_waveform_peaks_count",
 ]
 
 _lib = None
@@ -87,6 +88,12 @@ def lib() -> C.CDLL:
     L.flo_decode_device.argtypes = [vp, vp, sz, vp, sz, C.POINTER(sz), C.POINTER(Info)]
     L.flo_stream_encode_frames.restype = C.c_int
     L.flo_stream_encode_frames.argtypes = [vp, vp, sz, u32, u8, u8, u8, C.POINTER(vp), C.POINTER(sz), C.POINTER(vp), C.POINTER(u32)]
+    L.flo_waveform_peaks.restype = C.c_int
+    L.flo_waveform_peaks.argtypes = [vp, vp, sz, u32, u8, u32, C.POINTER(vp), C.POINTER(sz)]
+    L.flo_waveform_peaks_device.restype = C.c_int
+    L.flo_waveform_peaks_device.argtypes = [vp, vp, sz, u32, u8, u32, vp, sz, C.POINTER(sz)]
+    L.flo_waveform_peaks_count.restype = sz
+    L.flo_waveform_peaks_count.argtypes = [sz, u32, u8, u32]
     L.flo_host_alloc.restype = vp
     L.flo_host_alloc.argtypes = [sz]
     L.flo_host_free.restype = None

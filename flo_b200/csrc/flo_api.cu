@@ -6,6 +6,7 @@
 // lays the batch out (frame table, offsets that do not depend on the data), moves
 // buffers and launches.  There is no CPU implementation of any stage here.
 #include <algorithm>
+#include <cmath>
 #include <cstdarg>
 #include <cstdio>
 #include <cstdlib>
@@ -240,6 +241,7 @@ struct flo_ctx {
     DevBuf in, out, meta, tracks, frames, ctrl, fexcl, fsize, foff, plane, cres, report;
     DevBuf dec_frames, dec_units, dec_base, dec_ctl;      // decoder scratch
     DevBuf conv;                                           // f32 samples of the U8 / S32 ingest pre-pass
+    DevBuf peaks;                                          // waveform peaks (analysis metadata)
     DevBuf defer;                                          // per-CTA scratch of frames packed before their offset is known
     DevBuf crc_tab, fcrc;                                  // CRC tables for the encode kernel; raw CRC of every frame
     uint64_t counters[24] = {0};      // [0..7] analysis counters, [8..23] per-phase SM clock sums
@@ -332,7 +334,7 @@ extern "C" void flo_ctx_destroy(flo_ctx *c) {
     }
     if (c->persist_prev != (size_t)-1) { cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, c->persist_prev); cudaGetLastError(); }
     for (DevBuf *b : {&c->in, &c->out, &c->meta, &c->tracks, &c->frames, &c->ctrl, &c->fexcl, &c->fsize,
-                      &c->foff, &c->plane, &c->cres, &c->report, &c->crc_tab, &c->fcrc, &c->defer, &c->dec_frames, &c->dec_units, &c->dec_base, &c->dec_ctl, &c->conv})
+                      &c->foff, &c->plane, &c->cres, &c->report, &c->crc_tab, &c->fcrc, &c->defer, &c->peaks, &c->dec_frames, &c->dec_units, &c->dec_base, &c->dec_ctl, &c->conv})
         b->release();
     c->h_small.release();
     c->h_out.release();
@@ -990,6 +992,83 @@ extern "C" int flo_stream_encode_frames(flo_ctx *c, const float *samples, size_t
     flo_free(img);
     *out = buf; *out_len = w; *frame_off = offs; *n_frames = nf;
     return FLO_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// Waveform peaks of libflo::encode()'s analysis metadata (include/flo_b200.h: flo_waveform_peaks*)
+// ------------------------------------------------------------------------------------------------
+namespace {
+// analysis.rs:44-54: how many windows, and samples per window in f64.  A zero channel count or sample rate makes
+// the reference ask for a Vec of usize::MAX peaks (capacity overflow panic): an argument error here.
+int peaks_plan(size_t n, uint32_t sr, uint8_t ch, uint32_t pps, double *spp_out, size_t *total_out) {
+    *spp_out = 0.0; *total_out = 0;
+    if (ch == 0 || sr == 0) { set_err("waveform peaks: channels and sample_rate must be non-zero"); return FLO_ERR_ARG; }
+    if (n == 0) return FLO_OK;                                              // analysis.rs:44-50
+    const double spp = (double)sr / (double)pps;                            // +inf for peaks_per_second = 0: no peaks
+    const double t = std::ceil((double)n / (spp * (double)ch));
+    if (!(t < 1e12)) { set_err("waveform peaks: %g windows requested", t); return FLO_ERR_ARG; }
+    size_t total = t > 0 ? (size_t)t : 0;
+    // the loop leaves at the first window that starts behind the input (analysis.rs:65-67); starts never decrease
+    while (total > 0) {
+        const double s = (double)(total - 1) * spp;
+        const unsigned long long s0 = s >= 18446744073709551615.0 ? ~0ull : (unsigned long long)s;
+        if (s0 > (~0ull) / ch || s0 * ch >= n) total--;
+        else break;
+    }
+    *spp_out = spp; *total_out = total;
+    return FLO_OK;
+}
+int peaks_impl(flo_ctx *c, const float *h_x, const float *d_x, size_t n, uint32_t sr, uint8_t ch, uint32_t pps,
+               float *d_peaks_user, size_t cap, float **out, size_t *n_peaks) {
+    if (!c || !n_peaks || (n && !h_x && !d_x) || (h_x && !out)) { set_err("bad argument"); return FLO_ERR_ARG; }
+    *n_peaks = 0;
+    if (out) *out = nullptr;
+    double spp;
+    size_t total;
+    if (int rc = peaks_plan(n, sr, ch, pps, &spp, &total)) return rc;
+    if (total == 0) return FLO_OK;
+    if (d_peaks_user == nullptr && !out) { set_err("bad argument"); return FLO_ERR_ARG; }
+    if (!out && total > cap) { set_err("waveform peaks: %zu peaks, room for %zu", total, cap); return FLO_ERR_ARG; }
+    std::lock_guard<std::mutex> lk(c->mu);
+    DeviceGuard dg(c->device);
+    CK(dg.err);
+    cudaStream_t st = c->stream;
+    if (h_x) {
+        if (int rc = c->in.reserve(n * sizeof(float))) return rc;
+        CK(cudaMemcpyAsync(c->in.p, h_x, n * sizeof(float), cudaMemcpyHostToDevice, st));
+        d_x = (const float *)c->in.p;
+    } else if (((uintptr_t)d_x & 3u) != 0) { set_err("device samples pointer not aligned to the sample size"); return FLO_ERR_ARG; }
+    if (int rc = c->peaks.reserve(total * sizeof(float) + 16)) return rc;
+    flo::PeakParams pp;
+    pp.x = d_x; pp.n = n; pp.spp = spp; pp.channels = ch; pp.n_peaks = total;
+    pp.max_bits = (unsigned *)c->peaks.p;
+    pp.peaks = out ? (float *)((uint8_t *)c->peaks.p + 16) : d_peaks_user;
+    CK(flo::launch_waveform_peaks(pp, st));
+    if (out) {
+        float *h = (float *)malloc(total * sizeof(float));
+        if (!h) { cudaStreamSynchronize(st); set_err("out of host memory"); return FLO_ERR_NOMEM; }
+        cudaError_t e = cudaMemcpyAsync(h, pp.peaks, total * sizeof(float), cudaMemcpyDeviceToHost, st);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+        if (e != cudaSuccess) { free(h); cudaGetLastError(); set_err("waveform peaks: %s", cudaGetErrorString(e)); return FLO_ERR_CUDA; }
+        *out = h;
+    } else CK(cudaStreamSynchronize(st));
+    *n_peaks = total;
+    return FLO_OK;
+}
+}  // namespace
+
+extern "C" int flo_waveform_peaks(flo_ctx *c, const float *samples, size_t n, uint32_t sr, uint8_t ch, uint32_t pps, float **peaks, size_t *n_peaks) {
+    if (!peaks) { set_err("bad argument"); return FLO_ERR_ARG; }
+    return peaks_impl(c, samples, nullptr, n, sr, ch, pps, nullptr, 0, peaks, n_peaks);
+}
+extern "C" int flo_waveform_peaks_device(flo_ctx *c, const float *d_samples, size_t n, uint32_t sr, uint8_t ch, uint32_t pps,
+                                         float *d_peaks, size_t capacity, size_t *n_peaks) {
+    return peaks_impl(c, nullptr, d_samples, n, sr, ch, pps, d_peaks, capacity, nullptr, n_peaks);
+}
+extern "C" size_t flo_waveform_peaks_count(size_t n, uint32_t sr, uint8_t ch, uint32_t pps) {
+    double spp;
+    size_t total;
+    return peaks_plan(n, sr, ch, pps, &spp, &total) ? 0 : total;
 }
 
 // ------------------------------------------------------------------------------------------------

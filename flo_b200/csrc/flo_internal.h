@@ -121,6 +121,18 @@ void upload_crc_tables();
 // reflo's U8 / S32 ingest arms (reflo/src/audio.rs:255-269) as a pre-pass: interleaved PCM -> interleaved f32
 cudaError_t launch_ingest_convert(const void *src, float *dst, unsigned long long n, int format, cudaStream_t st);
 
+// waveform peaks of libflo::encode()'s analysis metadata (libflo/src/core/analysis.rs:38-119)
+struct PeakParams {
+    const float *x;                   // interleaved f32 samples
+    unsigned long long n;             // samples.len()
+    double spp;                       // samples_per_peak = sample_rate / peaks_per_second, in f64
+    uint32_t channels;
+    unsigned long long n_peaks;       // windows that start inside the input
+    float *peaks;                     // out
+    unsigned *max_bits;               // scratch: bit pattern of the largest peak
+};
+cudaError_t launch_waveform_peaks(const PeakParams &p, cudaStream_t st);     // 2 kernels
+
 // ---- lossless decoder (libflo/src/reader.rs + libflo/src/lossless/decoder.rs) ----
 enum DecErr : uint32_t { DEC_TOO_MANY = 1, DEC_BAD_ORDER = 2, DEC_EOF = 3, DEC_TRANSFORM = 4, DEC_BAD_K = 5 };
 struct DecFrame { uint32_t type_flags; uint32_t n; };          // type | flags << 8 ; frame_samples (0 past the reader's break)

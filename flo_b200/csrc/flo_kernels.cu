@@ -250,4 +250,68 @@ cudaError_t launch_ingest_convert(const void *src, float *dst, unsigned long lon
     return cudaGetLastError();
 }
 
+// ------------------------------------------------------------------------------------------------
+// libflo::encode()'s waveform peaks (libflo/src/core/analysis.rs:38-119), exact in f32:
+// window idx covers the sample frames [trunc(idx * spp), trunc((idx + 1) * spp)) with spp = sample_rate /
+// peaks_per_second in f64 (:52, :58-62); mono takes max |s| (:73-78), stereo the mean of the two channels'
+// max |s| over whole pairs (:80-91), any other channel count the maximum of the per-frame sample means, without
+// abs (:93-99); all peaks are then divided by the largest one (:104-110).  max, add, divide are IEEE operations,
+// so the result does not depend on the order the window is read in -- except the sequential f32 sum of the
+// many-channel arm, which one lane does in the reference's order.  One warp per window; the largest peak is
+// kept as the maximum of the bit patterns (peaks are >= 0).
+// ------------------------------------------------------------------------------------------------
+__global__ void k_waveform_peaks(const PeakParams p) {
+    const unsigned lane = threadIdx.x & 31u;
+    const u64 nwarps = ((u64)gridDim.x * blockDim.x) >> 5;
+    for (u64 idx = ((u64)blockIdx.x * blockDim.x + threadIdx.x) >> 5; idx < p.n_peaks; idx += nwarps) {
+        u64 s = __double2ull_rz(__dmul_rn((double)idx, p.spp));
+        u64 e = __double2ull_rz(__dmul_rn(__dadd_rn((double)idx, 1.0), p.spp));
+        s *= p.channels;
+        e = min(e * (u64)p.channels, p.n);
+        const float *w = p.x + s;
+        const u64 len = e > s ? e - s : 0;
+        float peak;
+        if (p.channels == 1) {
+            float m = 0.0f;
+            for (u64 i = lane; i < len; i += 32) m = fmaxf(m, fabsf(w[i]));
+            for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+            peak = m;
+        } else if (p.channels == 2) {
+            float l = 0.0f, r = 0.0f;
+            for (u64 i = lane; i < (len >> 1); i += 32) { l = fmaxf(l, fabsf(w[2 * i])); r = fmaxf(r, fabsf(w[2 * i + 1])); }
+            for (int o = 16; o > 0; o >>= 1) { l = fmaxf(l, __shfl_xor_sync(0xffffffffu, l, o)); r = fmaxf(r, __shfl_xor_sync(0xffffffffu, r, o)); }
+            peak = __fdiv_rn(__fadd_rn(l, r), 2.0f);
+        } else {
+            float m = 0.0f;
+            const u64 C = p.channels, nchunk = (len + C - 1) / C;
+            for (u64 q = lane; q < nchunk; q += 32) {
+                const u64 a = q * C, b = min(a + C, len);
+                float sum = 0.0f;
+                for (u64 i = a; i < b; i++) sum = __fadd_rn(sum, w[i]);
+                m = fmaxf(m, __fdiv_rn(sum, (float)(b - a)));
+            }
+            for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+            peak = m;
+        }
+        if (lane == 0) {
+            p.peaks[idx] = peak;
+            if (peak > 0.0f) atomicMax(p.max_bits, __float_as_uint(peak));
+        }
+    }
+}
+__global__ void k_normalise_peaks(float *peaks, u64 n, const unsigned *max_bits) {
+    const float mx = __uint_as_float(*max_bits);
+    if (!(mx > 0.0f)) return;                                                 // analysis.rs:105
+    for (u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (u64)gridDim.x * blockDim.x) peaks[i] = __fdiv_rn(peaks[i], mx);
+}
+cudaError_t launch_waveform_peaks(const PeakParams &p, cudaStream_t st) {
+    cudaError_t e = cudaMemsetAsync(p.max_bits, 0, 4, st);
+    if (e != cudaSuccess || p.n_peaks == 0) return e;
+    const u64 want = (p.n_peaks + 7) / 8;                                     // 8 warps (windows) per CTA
+    k_waveform_peaks<<<(unsigned)(want < 148ull * 8 ? want : 148ull * 8), 256, 0, st>>>(p);
+    const u64 w2 = (p.n_peaks + 255) / 256;
+    k_normalise_peaks<<<(unsigned)(w2 < 148ull ? w2 : 148ull), 256, 0, st>>>(p.peaks, p.n_peaks, p.max_bits);
+    return cudaGetLastError();
+}
+
 }  // namespace flo

@@ -172,6 +172,24 @@ int flo_decode(flo_ctx *ctx, const uint8_t *file, size_t len, float **out, size_
 int flo_decode_device(flo_ctx *ctx, const void *d_file, size_t len, float *d_out, size_t d_out_capacity,
                       size_t *n_interleaved, flo_info *info);
 
+/* -------------------------------------------------------------------------
+ * Waveform peaks of the analysis metadata libflo::encode() attaches.  Replaces
+ *   core::analysis::extract_waveform_peaks(samples, channels, sample_rate, peaks_per_second) -> WaveformData
+ * (libflo/src/core/analysis.rs:38-119; called from add_analysis_data_if_missing, libflo/src/lib.rs:219-241, with
+ * peaks_per_second = 50): *peaks holds WaveformData.peaks (library-allocated, flo_free), already normalised to
+ * the largest peak.  Every operation is an IEEE f32 max / add / divide, so the values are the reference's bit
+ * for bit (two unspecified corners: the sign of a zero peak for more than two channels, and the payload of the
+ * NaN an infinite largest peak leaves).  channels == 0 or sample_rate == 0 make the reference panic (capacity
+ * overflow): FLO_ERR_ARG.  peaks_per_second == 0 or no samples: zero peaks.
+ * The spectral fingerprint and EBU R128 parts of that metadata, and its MessagePack serialisation, are not
+ * provided. */
+int flo_waveform_peaks(flo_ctx *ctx, const float *samples, size_t n_interleaved, uint32_t sample_rate,
+                       uint8_t channels, uint32_t peaks_per_second, float **peaks, size_t *n_peaks);
+/* device-resident samples and peaks (capacity in floats; flo_waveform_peaks_count gives the count needed) */
+int flo_waveform_peaks_device(flo_ctx *ctx, const float *d_samples, size_t n_interleaved, uint32_t sample_rate,
+                              uint8_t channels, uint32_t peaks_per_second, float *d_peaks, size_t capacity, size_t *n_peaks);
+size_t flo_waveform_peaks_count(size_t n_interleaved, uint32_t sample_rate, uint8_t channels, uint32_t peaks_per_second);
+
 /* Pinned host memory (optional).  Page-locked inputs go to the copy engine
  * directly; pageable inputs (a plain Rust slice) are staged by the library
  * through its own pinned ring with several copy threads (FLO_B200_COPY_THREADS

@@ -224,3 +224,36 @@ def test_empty_and_nan_inputs():
     out = oracle.encode(x, 100, 1, 16, 5, b"")
     got = oracle.decode_i32(out)
     assert got[:4].tolist() == [0, 32767, -32768, 8191]
+
+
+# ---- waveform peaks (libflo/src/core/analysis.rs:38-119): PARITY UNPINNED -- the reference's tests hold properties
+# only (libflo/tests/rust/analysis_tests.rs:3-67); these are those properties on its inputs plus hand-derived answers
+def test_waveform_peaks_reference_properties_unpinned():
+    import flo_analysis
+    samples = np.array([0.5, -0.3, 0.8, -0.2, 0.1, -0.9], np.float32)          # analysis_tests.rs:5, :21
+    for ch in (1, 2):
+        p = flo_analysis.extract_waveform_peaks(samples, ch, 44100, 10)
+        assert p.size == 1 and p[0] == np.float32(1.0)                          # one window; normalised to itself
+        assert np.array_equal(p, flo_analysis.extract_waveform_peaks(samples, ch, 44100, 10))
+    assert flo_analysis.extract_waveform_peaks(np.zeros(0, np.float32), 1, 44100, 10).size == 0   # :34-41
+
+
+def test_waveform_peaks_hand_derived_unpinned():
+    import flo_analysis
+    f = np.float32
+    p = flo_analysis.extract_waveform_peaks([0.5, -0.25, 0.125, 1.0, -0.75], 1, 4, 2)             # windows of 2
+    assert p.tolist() == [0.5, 1.0, 0.75]
+    p = flo_analysis.extract_waveform_peaks([0.5, -0.25, 0.25, 0.75, 1.0, 0.0, -0.5], 2, 2, 1)    # odd tail dropped
+    assert p.tolist() == [1.0, float(f(0.5) / f(0.625))]
+    p = flo_analysis.extract_waveform_peaks([0.3, 0.3, 0.3, -1, -1, -1, 0.6, 0.0], 3, 1, 1)       # means, no abs
+    m0 = f(f(f(f(0.3) + f(0.3)) + f(0.3)) / f(3))
+    assert p.tolist() == [1.0, 0.0, float(f(f(f(0.6) / f(2)) / m0))]
+    # 2.5 sample frames per peak: windows [0,2) [2,5) [5,7) [7,10)
+    p = flo_analysis.extract_waveform_peaks(np.arange(1, 11, dtype=np.float32), 1, 5, 2)
+    assert p.tolist() == [float(f(v) / f(10)) for v in (2, 5, 7, 10)]
+    assert flo_analysis.extract_waveform_peaks([1.0, 2.0], 1, 44100, 0).size == 0                 # spp = inf: no window
+    assert flo_analysis.extract_waveform_peaks([0.0, 0.0, 0.0], 1, 1, 1).tolist() == [0.0, 0.0, 0.0]   # nothing to normalise by
+    nan = float("nan")
+    assert flo_analysis.extract_waveform_peaks([nan, 0.5, nan, nan], 1, 2, 1).tolist() == [1.0, 0.0]  # f32::max skips NaN
+    with pytest.raises(OverflowError):
+        flo_analysis.extract_waveform_peaks([1.0], 0, 44100, 10)
