@@ -566,7 +566,8 @@ static int encode_batch_impl(flo_ctx *c, const flo_track *tracks, size_t n_track
     // Shared memory of a CTA: its fixed state, a work area (ingest stages of the bulk async copies, then the
     // packer's 16 KB staging ring) and, when they fit, the sample planes.  A stage is one step of all threads.
     auto work_min = [&](const EncodeVariant &v) { return (size_t)v.threads * 64; };   // one 2 KB ring per warp
-    auto share_of = [&](const EncodeVariant &v) { return v.ctas_per_sm > 1 ? c->smem_optin / v.ctas_per_sm - 1024 : c->smem_optin; };
+    auto ctas_of = [&](const EncodeVariant &v) { return level < 4 ? v.ctas_fixed : v.ctas_per_sm; };   // levels 0-3: the instantiation without LPC
+    auto share_of = [&](const EncodeVariant &v) { return ctas_of(v) > 1 ? c->smem_optin / ctas_of(v) - 1024 : c->smem_optin; };
     auto stage_of = [&](const EncodeVariant &v) { return (size_t)v.threads * (v.threads >= 512 ? 4 : 8) * (size_t)std::max<uint64_t>(L.max_group_bytes, 2); };
     auto fits = [&](const EncodeVariant &v) { return v.static_smem() + plane_bytes + std::max(work_min(v), 2 * stage_of(v)) <= share_of(v); };
     const EncodeVariant *var = &encode_variant(512);
@@ -583,7 +584,7 @@ static int encode_batch_impl(flo_ctx *c, const flo_track *tracks, size_t n_track
     size_t dyn, plane_cap;
     if (planes_in_smem) { dyn = share_of(*var); plane_cap = dyn - smem_static - work; }
     else { dyn = smem_static + work; plane_cap = 0; }                     // global (L2) planes
-    const int ctas_per_sm = var->ctas_per_sm;
+    const int ctas_per_sm = ctas_of(*var);
     if (getenv("FLO_B200_DEBUG_OCC"))
         fprintf(stderr, "flo_b200: variant %d x %d, dyn smem %zu, occupancy %d\n", var->threads, ctas_per_sm, dyn, var->occupancy(dyn));
     int grid = (int)std::min<uint64_t>(std::max<uint64_t>(NF, 1), (uint64_t)c->sm_count * ctas_per_sm);

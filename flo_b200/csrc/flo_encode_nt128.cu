@@ -6,6 +6,7 @@
 
 #define FLO_VARIANT_NT 128
 #define FLO_VARIANT_CTAS 4
+#define FLO_VARIANT_CTAS_FIXED FLO_VARIANT_CTAS
 
 namespace flo {
 namespace nt128 {
@@ -19,7 +20,7 @@ typedef int32_t i32;
 
 }  // namespace nt128
 
-extern const EncodeVariant g_variant_nt128 = {128, 4, nt128::encode_static_smem, nt128::variant_configure,
+extern const EncodeVariant g_variant_nt128 = {128, FLO_VARIANT_CTAS, FLO_VARIANT_CTAS_FIXED, nt128::encode_static_smem, nt128::variant_configure,
                                               nt128::variant_launch, nt128::variant_occupancy};
 
 }  // namespace flo

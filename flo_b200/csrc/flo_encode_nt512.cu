@@ -6,6 +6,7 @@
 
 #define FLO_VARIANT_NT 512
 #define FLO_VARIANT_CTAS 1
+#define FLO_VARIANT_CTAS_FIXED FLO_VARIANT_CTAS
 
 namespace flo {
 namespace nt512 {
@@ -19,7 +20,7 @@ typedef int32_t i32;
 
 }  // namespace nt512
 
-extern const EncodeVariant g_variant_nt512 = {512, 1, nt512::encode_static_smem, nt512::variant_configure,
+extern const EncodeVariant g_variant_nt512 = {512, FLO_VARIANT_CTAS, FLO_VARIANT_CTAS_FIXED, nt512::encode_static_smem, nt512::variant_configure,
                                               nt512::variant_launch, nt512::variant_occupancy};
 
 }  // namespace flo

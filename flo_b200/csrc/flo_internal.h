@@ -103,6 +103,7 @@ struct FinalParams {
 struct EncodeVariant {
     int threads;                      // threads per CTA
     int ctas_per_sm;                  // CTAs this variant is built to co-reside per SM (register budget)
+    int ctas_fixed;                   // the same for the instantiation without LPC (levels 0-3), which needs fewer registers
     size_t (*static_smem)();          // bytes of the kernel's own shared state (in front of the planes)
     cudaError_t (*configure)(size_t dyn_smem);
     cudaError_t (*launch)(const EncodeParams &p, int grid, size_t dyn_smem, cudaStream_t st);

