@@ -19,6 +19,12 @@
 constexpr int NT = FLO_VARIANT_NT;
 constexpr int NWARP = NT / 32;
 
+#ifndef FLO_SINGLE_BS
+#define FLO_SINGLE_BS 4       // samples per block of a one-order FIR sweep (independent chains)
+#endif
+#ifndef FLO_PAIR_SWEEPS
+#define FLO_PAIR_SWEEPS 0     // 1: two LPC orders per sweep share one window (fewer loads, but the second set of chains and
+#endif                        //    coefficients spills ~1.5 KB per thread at 128 registers: 3.13 vs 3.08 ms at level 5)
 #ifndef FLO_PAIR_BS
 #define FLO_PAIR_BS 4         // samples per block of the two-order FIR sweeps (independent chains = 2 x this)
 #endif
@@ -636,9 +642,9 @@ struct Sweeps {
     static __device__ __forceinline__ void run(const ChanState &cs, const i32 (&x)[NH + CH], LpcStat *st /* by order - LO0 */, int lo0) {
         if constexpr (LO <= HI) {
             // two orders per sweep while their taps fit the register file (13 coefficients), else one
-            constexpr bool PAIR = LO < HI && HI + LO <= 13;
+            constexpr bool PAIR = FLO_PAIR_SWEEPS && LO < HI && HI + LO <= 13;
             constexpr int OA = HI, OB = PAIR ? LO : 0;
-            constexpr int BS = PAIR ? FLO_PAIR_BS : 4;
+            constexpr int BS = PAIR ? FLO_PAIR_BS : FLO_SINGLE_BS;
             const bool oka = cs.lpc_ok[OA - 5] != 0, okb = OB > 0 && cs.lpc_ok[(OB > 0 ? OB : 5) - 5] != 0;
             if (oka || okb) {
                 LpcStat a = st[OA - lo0], b = st[(OB > 0 ? OB : OA) - lo0];
