@@ -415,9 +415,16 @@ __device__ __forceinline__ void fixed_chunk(const i32 *x, F &&fn) {
 // int -> f64 on the conversion pipe.  `volatile` pins each conversion where it is written, so the
 // compiler neither keeps a whole chunk of doubles alive (spills) nor re-converts a sample per use.
 __device__ __forceinline__ double cvt_f64(i32 x) {
+#ifdef FLO_CVT_MAGIC
+    // experiment: 2^52 + 2^31 + x built from its bit pattern, minus the constant -- one ALU and one FP64-pipe
+    // instruction instead of I2F.F64 on the XU pipe; exact for every i32.  Measured slower (3.20 vs 3.07 ms at level 5):
+    // the XU pipe (22 % busy) is not what the kernel waits for, the extra issue slots are.  Off.
+    return __dadd_rn(__hiloint2double(0x43300000, (int)((u32)x ^ 0x80000000u)), -4503601774854144.0);
+#else
     double d;
     asm volatile("cvt.rn.f64.s32 %0, %1;" : "=d"(d) : "r"(x));
     return d;
+#endif
 }
 
 // calc_residuals_int, lpc.rs:279-298, on the FP64 pipe, for LPC orders OA and OB (OB = 0: one order) over
