@@ -1645,8 +1645,11 @@ static_assert(sizeof(ChanResult) % 4 == 0, "ChanResult is copied word by word");
 // ----------------------------------------------------------------------------
 extern __shared__ __align__(128) unsigned char dyn_smem[];
 
+#ifndef FLO_LB_THREADS
+#define FLO_LB_THREADS NT        // experiments: a larger value lowers the register bound without changing the launch
+#endif
 template <int P>
-__global__ void __launch_bounds__(NT, P == 0 ? FLO_VARIANT_CTAS_FIXED : FLO_VARIANT_CTAS) k_encode_frames(const EncodeParams p) {
+__global__ void __launch_bounds__(FLO_LB_THREADS, P == 0 ? FLO_VARIANT_CTAS_FIXED : FLO_VARIANT_CTAS) k_encode_frames(const EncodeParams p) {
     Smem &s = *reinterpret_cast<Smem *>(dyn_smem);
     unsigned char *work = dyn_smem + SMEM_HDR;
     u32 *ring = reinterpret_cast<u32 *>(work);

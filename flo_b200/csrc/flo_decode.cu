@@ -49,6 +49,11 @@ __global__ void k_dec_parse(DecodeParams p) {
         const unsigned long long payload = pos + 4, ch_end = payload + ch_size;
         if (n > 2000000u) { dec_fail(p.ctl, i, c + 1, DEC_TOO_MANY); break; }       // reader.rs:175-177
         if (type >= 1 && type <= 12) {
+            // the reader's own order of checks (reader.rs:208-214): the order byte is read and tested before anything
+            // behind it is touched, and Reader::read meets every frame before the decoder runs -- so a bad order in an
+            // earlier frame wins over a truncated later one, and over a truncated payload of the same channel
+            if (payload + 1 > p.len) { dec_fail(p.ctl, i, c + 1, DEC_EOF); break; }
+            if (f[payload] > 12) { dec_fail(p.ctl, i, c + 1, DEC_BAD_ORDER); break; }
             if (ch_end > p.len) { dec_fail(p.ctl, i, c + 1, DEC_EOF); break; }       // header or residual read runs off the file
         } else if (type == FT_RAW) {
             const unsigned long long need = 2ull * n;

@@ -249,7 +249,14 @@ def test_frame_level_errors(fb):
     cases = [(build_file(1, [(1, n, 0, [ch]), (3, n, 0, [bytes([13]) + ch[1:]])]), "Invalid LPC order"),
              (build_file(1, [(1, 2000001, 0, [ch])]), "Invalid frame: too many samples"),
              (build_file(1, [(1, n, 0, [ch]), (1, n, 0, [ch])])[:-3], "Unexpected end of file"),
-             (build_file(2, [(1, n, 0, [ch])]), "Unexpected end of file")]                 # second channel missing
+             (build_file(2, [(1, n, 0, [ch])]), "Unexpected end of file"),                 # second channel missing
+             # two errors in one file: the reader meets the bad order of frame 1 before the truncated frame 2 ...
+             (build_file(1, [(1, n, 0, [ch]), (3, n, 0, [bytes([13]) + ch[1:]]), (1, n, 0, [ch])])[:-3], "Invalid LPC order"),
+             # ... and inside one channel the order byte is tested before its payload is found to run off the file
+             (build_file(1, [(1, n, 0, [ch]), (3, n, 0, [bytes([13]) + ch[1:]])])[:-5], "Invalid LPC order"),
+             # the other way round: a truncated frame 1 in front of a bad order in frame 2 cannot be built (frames are
+             # contiguous), but a frame that claims too many samples in front of a bad order reports the former
+             (build_file(1, [(1, 2000001, 0, [ch]), (3, n, 0, [bytes([13]) + ch[1:]])]), "Invalid frame: too many samples")]
     for data, msg in cases:
         with pytest.raises(ValueError) as eo:
             oracle.decode(data)
