@@ -103,11 +103,6 @@ __device__ __forceinline__ u32 multmodp(u32 a, u32 b) {
     }
     return p;
 }
-__device__ u32 x2nmodp(u64 n, unsigned k) {
-    u32 p = 1u << 31;
-    while (n) { if (n & 1) p = multmodp(c_x2n[k & 31], p); n >>= 1; k++; }
-    return p;
-}
 
 // ----------------------------------------------------------------------------
 // setup / finalise kernels
@@ -155,17 +150,31 @@ __global__ void k_write_toc(const FinalParams p) {
 // CRC32 of the DATA chunk (crc32.rs:23-30, writer.rs:58).  The raw CRC R(M) = M(x) x^32 mod p is linear and
 // ignores leading zeros, so the DATA chunk's CRC is the XOR of every frame's R shifted by the bytes that
 // follow the frame in the chunk.  The encode kernel leaves R(frame) in frame_crc (computed from the frame's bytes
-// while they are still in L2); this kernel only applies the shifts: one thread per frame.
-// multmodp / x2nmodp above follow zlib's crc32_combine helpers (zlib 1.2.12+, crc32.c; (C) 1995-2022 Mark Adler,
+// while they are still in L2); this kernel only applies the shifts: one warp per frame.
+// multmodp above and the x^(2^k) table follow zlib's crc32_combine helpers (zlib 1.2.12+, crc32.c; (C) 1995-2022 Mark Adler,
 // zlib licence), re-typed here.
+// x^(8 n) mod p for a byte count n, by a whole warp: lane b holds the factor of bit b of n (x^(8 * 2^b) from
+// c_x2n, whose index wraps with period 32 like zlib's x2nmodp), five rounds of multmodp fold the 32 factors.
+// The one-thread form walks up to 32 dependent multmodp's (40 us for the 3600 frames of an hour, divergent).
+__device__ __forceinline__ u32 warp_x8n(u64 n) {
+    const unsigned lane = threadIdx.x & 31u;
+    const u32 t = c_x2n[(lane + 3u) & 31u];
+    u32 f = ((n >> lane) & 1ull) ? t : 0x80000000u;                 // 0x80000000 = x^0
+    if ((n >> (32u + lane)) & 1ull) f = multmodp(f, t);              // bit 32 + b: same table entry
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) f = multmodp(f, __shfl_xor_sync(0xffffffffu, f, o));
+    return f;
+}
+// one warp per frame
 __global__ void k_crc_frames(const FinalParams p) {
-    const u32 g = blockIdx.x * blockDim.x + threadIdx.x;
+    const u32 g = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     if (g >= p.n_frames) return;
     const uint2 fd = p.frames[g];
     const TrackDev tr = p.tracks[fd.x];
     const u64 e1 = excl_at(p, tr.first_frame + tr.n_frames);
     const u64 after = e1 - (p.frame_excl[g] + p.frame_size[g]);
-    atomicXor(&p.track_crc[fd.x], multmodp(x2nmodp(after, 3), p.frame_crc[g]));
+    const u32 sh = warp_x8n(after);
+    if ((threadIdx.x & 31u) == 0) atomicXor(&p.track_crc[fd.x], multmodp(sh, p.frame_crc[g]));
 }
 
 // write_header_ex, writer.rs:132-191, + metadata (writer.rs:96): one block per track
@@ -177,9 +186,11 @@ __global__ void k_write_headers(const FinalParams p) {
     const u64 file0 = tr.static_off + e0;
     const u64 toc_size = 4 + 20ull * tr.n_frames;
     uint8_t *o = p.out + file0;
+    u32 xd = 0;
+    if (threadIdx.x < 32) xd = warp_x8n(dsize);
     if (threadIdx.x == 0) {
         // crc(M) = ~(R(M) ^ 0xFFFFFFFF x^(8 |M|)): initial state and final complement of crc32.rs:24-29
-        const u32 crc = ~(p.track_crc[t] ^ multmodp(x2nmodp(dsize, 3), 0xFFFFFFFFu));
+        const u32 crc = ~(p.track_crc[t] ^ multmodp(xd, 0xFFFFFFFFu));
         o[0] = 0x46; o[1] = 0x4C; o[2] = 0x4F; o[3] = 0x21;        // "FLO!", types.rs:6
         o[4] = 1; o[5] = 2;                                        // version 1.2, types.rs:12-13
         o[6] = 0; o[7] = 0;                                        // flags: lossless
@@ -219,7 +230,7 @@ cudaError_t launch_toc(const FinalParams &p, cudaStream_t st) {
 }
 cudaError_t launch_crc_frames(const FinalParams &p, cudaStream_t st) {
     if (p.n_frames == 0) return cudaSuccess;
-    k_crc_frames<<<(p.n_frames + 127) / 128, 128, 0, st>>>(p);
+    k_crc_frames<<<(p.n_frames + 7) / 8, 256, 0, st>>>(p);
     return cudaGetLastError();
 }
 cudaError_t launch_headers(const FinalParams &p, cudaStream_t st) {
