@@ -43,6 +43,7 @@ EXPORTS = [
     "flo_ctx_last_counters", "flo_ctx_enable_report", "flo_ctx_read_report", "flo_host_alloc", "flo_host_free", "flo_free",
     "flo_last_error", "flo_version", "flo_device_count", "flo_decode", "flo_decode_device", "flo_stream_encode_frames",
     "flo_waveform_peaks", "flo_waveform_peaks_device", "flo_waveform_peaks_count",
+    "flo_integrated_loudness", "flo_integrated_loudness_device",
 ]
 
 _lib = None
@@ -94,6 +95,10 @@ def lib() -> C.CDLL:
     L.flo_waveform_peaks_device.argtypes = [vp, vp, sz, u32, u8, u32, vp, sz, C.POINTER(sz)]
     L.flo_waveform_peaks_count.restype = sz
     L.flo_waveform_peaks_count.argtypes = [sz, u32, u8, u32]
+    L.flo_integrated_loudness.restype = C.c_int
+    L.flo_integrated_loudness.argtypes = [vp, vp, sz, u32, u8, C.POINTER(C.c_double)]
+    L.flo_integrated_loudness_device.restype = C.c_int
+    L.flo_integrated_loudness_device.argtypes = [vp, vp, sz, u32, u8, C.POINTER(C.c_double)]
     L.flo_host_alloc.restype = vp
     L.flo_host_alloc.argtypes = [sz]
     L.flo_host_free.restype = None

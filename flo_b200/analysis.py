@@ -46,3 +46,28 @@ def extract_waveform_peaks_device(d_samples: int, n_interleaved: int, channels: 
 
 def peaks_count(n_interleaved: int, sample_rate: int, channels: int, peaks_per_second: int) -> int:
     return int(_lib.lib().flo_waveform_peaks_count(int(n_interleaved), int(sample_rate), int(channels), int(peaks_per_second)))
+
+
+@dataclass
+class LoudnessMetrics:
+    """core/ebu_r128.rs LoudnessMetrics; only integrated_lufs is computed (the one value libflo::encode() stores)"""
+    integrated_lufs: float
+    loudness_range_lu: float = None
+    true_peak_dbtp: float = None
+    sample_peak_dbfs: float = None
+
+
+def compute_ebu_r128_loudness(samples, channels: int, sample_rate: int, ctx=None) -> LoudnessMetrics:
+    """Same arguments as the reference (libflo/src/core/ebu_r128.rs:182-186)."""
+    x = np.ascontiguousarray(samples, dtype=np.float32).reshape(-1)
+    ctx = ctx or default_context(0)
+    v = C.c_double()
+    _lib.check(ctx._L.flo_integrated_loudness(ctx._h, x.ctypes.data_as(C.c_void_p), x.size, int(sample_rate), int(channels), C.byref(v)))
+    return LoudnessMetrics(float(v.value))
+
+
+def integrated_loudness_device(d_samples: int, n_interleaved: int, channels: int, sample_rate: int, ctx=None) -> float:
+    ctx = ctx or default_context(0)
+    v = C.c_double()
+    _lib.check(ctx._L.flo_integrated_loudness_device(ctx._h, C.c_void_p(d_samples), int(n_interleaved), int(sample_rate), int(channels), C.byref(v)))
+    return float(v.value)

@@ -134,6 +134,20 @@ struct PeakParams {
 };
 cudaError_t launch_waveform_peaks(const PeakParams &p, cudaStream_t st);     // 2 kernels
 
+// K-weighted hop energies for the EBU R128 integrated loudness of libflo::encode()'s metadata (core/ebu_r128.rs)
+struct KwParams {
+    const float *x;                   // interleaved f32 samples
+    unsigned long long frames;        // sample frames per channel
+    uint32_t channels;
+    uint32_t hop;                     // frames per 100 ms hop (= one segment of the filter)
+    unsigned long long n_hops;        // ceil(frames / hop)
+    double co[10];                    // shelf b0 b1 b2 a1 a2 | high-pass b0 b1 b2 a1 a2 (ebu_r128.rs:58-102)
+    double *state;                    // [channels][n_hops][4]: pass 1 writes the segment's final state from a zero start,
+                                      // pass 2 reads the true start state from the same slots (rewritten by the host scan)
+    double *hop_sum;                  // [channels][n_hops]: sum of y^2 over the hop (pass 2)
+};
+cudaError_t launch_kweight(const KwParams &p, int pass, cudaStream_t st);
+
 // ---- lossless decoder (libflo/src/reader.rs + libflo/src/lossless/decoder.rs) ----
 enum DecErr : uint32_t { DEC_TOO_MANY = 1, DEC_BAD_ORDER = 2, DEC_EOF = 3, DEC_TRANSFORM = 4, DEC_BAD_K = 5 };
 struct DecFrame { uint32_t type_flags; uint32_t n; };          // type | flags << 8 ; frame_samples (0 past the reader's break)

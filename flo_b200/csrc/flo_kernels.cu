@@ -284,12 +284,19 @@ __global__ void k_waveform_peaks(const PeakParams p) {
         float peak;
         if (p.channels == 1) {
             float m = 0.0f;
-            for (u64 i = lane; i < len; i += 32) m = fmaxf(m, fabsf(w[i]));
+#pragma unroll 4
+            for (u64 i = lane; i < len; i += 32) m = fmaxf(m, fabsf(__ldg(w + i)));
             for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
             peak = m;
         } else if (p.channels == 2) {
             float l = 0.0f, r = 0.0f;
-            for (u64 i = lane; i < (len >> 1); i += 32) { l = fmaxf(l, fabsf(w[2 * i])); r = fmaxf(r, fabsf(w[2 * i + 1])); }
+            if (((uintptr_t)w & 7u) == 0) {                    // pairs as 8-byte loads (the window starts on a left sample)
+                const float2 *w2 = reinterpret_cast<const float2 *>(w);
+#pragma unroll 4
+                for (u64 i = lane; i < (len >> 1); i += 32) { const float2 q = __ldg(w2 + i); l = fmaxf(l, fabsf(q.x)); r = fmaxf(r, fabsf(q.y)); }
+            } else {
+                for (u64 i = lane; i < (len >> 1); i += 32) { l = fmaxf(l, fabsf(w[2 * i])); r = fmaxf(r, fabsf(w[2 * i + 1])); }
+            }
             for (int o = 16; o > 0; o >>= 1) { l = fmaxf(l, __shfl_xor_sync(0xffffffffu, l, o)); r = fmaxf(r, __shfl_xor_sync(0xffffffffu, r, o)); }
             peak = __fdiv_rn(__fadd_rn(l, r), 2.0f);
         } else {
@@ -322,6 +329,130 @@ cudaError_t launch_waveform_peaks(const PeakParams &p, cudaStream_t st) {
     k_waveform_peaks<<<(unsigned)(want < 148ull * 8 ? want : 148ull * 8), 256, 0, st>>>(p);
     const u64 w2 = (p.n_peaks + 255) / 256;
     k_normalise_peaks<<<(unsigned)(w2 < 148ull ? w2 : 148ull), 256, 0, st>>>(p.peaks, p.n_peaks, p.max_bits);
+    return cudaGetLastError();
+}
+
+// ------------------------------------------------------------------------------------------------
+// EBU R128 integrated loudness of libflo::encode()'s metadata (libflo/src/core/ebu_r128.rs):
+// the K-weighting (two cascaded biquads per channel, :43-48, :105-109) is a serial recurrence over the whole
+// channel in the reference.  Here a channel is cut into its 100 ms hops; pass 1 runs every hop from a zero state
+// and keeps the final state (the forced response), the host chains the hops' start states with the 4 x 4
+// transition matrix of one hop (s' = M s + forced), and pass 2 runs every hop again from its true start state and
+// sums y^2 -- exactly the reference's operations inside a hop (separately rounded products and sums, same
+// order), so the only differences from the sequential result are the rounding of the chained start states and
+// the regrouping of a block's sum into its four hops: ~1e-13 LU (tolerance stated in tests/test_gpu_analysis.py).
+// One thread per (channel, hop), a CTA of 32 hops x C channels.  The samples of the CTA's hops are staged through
+// shared memory 32 frames at a time -- every warp reads whole 128-byte pieces of a hop's interleaved frames and
+// stores them transposed ([float index within the tile][hop], row stride 33: conflict-free both ways) -- because a
+// serial filter per thread would otherwise touch 32 different lines with every load of a warp.
+// ------------------------------------------------------------------------------------------------
+constexpr int KW_HOPS = 32;           // hops per CTA (= lanes of a warp; warp = channel)
+constexpr int KW_T = 32;              // frames per staged tile
+constexpr int KW_MAXC = 8;            // more channels than this: the unstaged kernel
+
+struct KwFilter {
+    double z1s = 0.0, z2s = 0.0, z1h = 0.0, z2h = 0.0, acc = 0.0;
+    template <int PASS>
+    __device__ __forceinline__ void step(const double (&co)[10], double v) {
+        const double y1 = __dadd_rn(__dmul_rn(co[0], v), z1s);                                 // Biquad::process, shelf
+        z1s = __dadd_rn(__dsub_rn(__dmul_rn(co[1], v), __dmul_rn(co[3], y1)), z2s);
+        z2s = __dsub_rn(__dmul_rn(co[2], v), __dmul_rn(co[4], y1));
+        const double y = __dadd_rn(__dmul_rn(co[5], y1), z1h);                                 // high-pass
+        z1h = __dadd_rn(__dsub_rn(__dmul_rn(co[6], y1), __dmul_rn(co[8], y)), z2h);
+        z2h = __dsub_rn(__dmul_rn(co[7], y1), __dmul_rn(co[9], y));
+        if (PASS == 2) acc = __dadd_rn(acc, __dmul_rn(y, y));                                  // ebu_r128.rs:248-250
+    }
+};
+
+template <int PASS>
+__global__ void k_kweight_staged(const KwParams p) {
+    extern __shared__ float kw_tile[];                     // [KW_T * C][33]
+    const u32 C = p.channels;
+    const u32 lane = threadIdx.x & 31u, ch = threadIdx.x >> 5;          // blockDim = 32 * C
+    const u64 j0 = (u64)blockIdx.x * KW_HOPS, j = j0 + lane;
+    const bool live = j < p.n_hops;
+    const u64 tseg = (u64)ch * p.n_hops + j;
+    double co[10];
+#pragma unroll
+    for (int i = 0; i < 10; i++) co[i] = p.co[i];
+    KwFilter f;
+    if (PASS == 2 && live) { const double *st = p.state + (tseg << 2); f.z1s = st[0]; f.z2s = st[1]; f.z1h = st[2]; f.z2h = st[3]; }
+    const u64 my0 = j * p.hop, my1 = live ? min(my0 + p.hop, p.frames) : my0;
+    const u32 tid = threadIdx.x;                           // blockDim = 32 * C = floats of one hop's tile
+    const bool cta_full = j0 + KW_HOPS <= p.n_hops && (j0 + KW_HOPS) * p.hop <= p.frames;
+    const u64 hop_floats = (u64)p.hop * C;
+    // stage: iteration h = hop h of the CTA, thread tid = float tid of its frames [base, base + KW_T); all 32 loads of
+    // a thread are issued back to back, and the loads of tile b + 1 are in flight while tile b is filtered
+    float v[KW_HOPS];
+    auto load_tile = [&](u32 base) {
+        const float *src = p.x + (j0 * p.hop + base) * C + tid;
+        if (cta_full && base + KW_T <= p.hop) {
+#pragma unroll
+            for (int h = 0; h < KW_HOPS; h++) v[h] = __ldg(src + h * hop_floats);
+        } else {
+#pragma unroll
+            for (int h = 0; h < KW_HOPS; h++) {
+                const u64 hj = j0 + h;
+                const u64 f0 = hj * p.hop + base;
+                const u64 f1 = hj < p.n_hops ? min(min(f0 + KW_T, (hj + 1) * p.hop), p.frames) : f0;
+                const u64 nfl = f1 > f0 ? (f1 - f0) * C : 0;
+                v[h] = tid < nfl ? __ldg(src + h * hop_floats) : 0.0f;
+            }
+        }
+    };
+    load_tile(0);
+    for (u32 base = 0; base < p.hop; base += KW_T) {
+        __syncthreads();
+#pragma unroll
+        for (int h = 0; h < KW_HOPS; h++) kw_tile[tid * 33 + h] = v[h];
+        __syncthreads();
+        if (base + KW_T < p.hop) load_tile(base + KW_T);
+        const u64 fb = my0 + base;
+        const u32 nst = fb < my1 ? (u32)min((u64)KW_T, my1 - fb) : 0u;
+        if (nst == KW_T) {
+#pragma unroll 8
+            for (u32 i = 0; i < KW_T; i++) f.step<PASS>(co, (double)kw_tile[(i * C + ch) * 33 + lane]);
+        } else {
+            for (u32 i = 0; i < nst; i++) f.step<PASS>(co, (double)kw_tile[(i * C + ch) * 33 + lane]);
+        }
+    }
+    if (!live) return;
+    if (PASS == 1) { double *st = p.state + (tseg << 2); st[0] = f.z1s; st[1] = f.z2s; st[2] = f.z1h; st[3] = f.z2h; }
+    else p.hop_sum[tseg] = f.acc;
+}
+
+// unstaged form for more than KW_MAXC channels: one thread per (channel, hop), loads straight from global
+template <int PASS>
+__global__ void k_kweight(const KwParams p) {
+    const u64 t = (u64)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= p.n_hops * p.channels) return;
+    const u32 ch = (u32)(t / p.n_hops);
+    const u64 j = t % p.n_hops;
+    const u64 i0 = j * p.hop, i1 = min(i0 + p.hop, p.frames);
+    double *st = p.state + (t << 2);
+    double co[10];
+#pragma unroll
+    for (int i = 0; i < 10; i++) co[i] = p.co[i];
+    KwFilter f;
+    if (PASS == 2) { f.z1s = st[0]; f.z2s = st[1]; f.z1h = st[2]; f.z2h = st[3]; }
+    const float *x = p.x + i0 * p.channels + ch;
+    for (u64 i = i0; i < i1; i++, x += p.channels) f.step<PASS>(co, (double)__ldg(x));
+    if (PASS == 1) { st[0] = f.z1s; st[1] = f.z2s; st[2] = f.z1h; st[3] = f.z2h; }
+    else p.hop_sum[t] = f.acc;
+}
+cudaError_t launch_kweight(const KwParams &p, int pass, cudaStream_t st) {
+    const u64 n = p.n_hops * p.channels;
+    if (n == 0) return cudaSuccess;
+    if (p.channels <= KW_MAXC) {
+        const unsigned grid = (unsigned)((p.n_hops + KW_HOPS - 1) / KW_HOPS), threads = 32u * p.channels;
+        const size_t smem = sizeof(float) * KW_T * p.channels * 33;
+        if (pass == 1) k_kweight_staged<1><<<grid, threads, smem, st>>>(p);
+        else k_kweight_staged<2><<<grid, threads, smem, st>>>(p);
+    } else {
+        const unsigned grid = (unsigned)((n + 127) / 128);
+        if (pass == 1) k_kweight<1><<<grid, 128, 0, st>>>(p);
+        else k_kweight<2><<<grid, 128, 0, st>>>(p);
+    }
     return cudaGetLastError();
 }
 

@@ -190,6 +190,19 @@ int flo_waveform_peaks_device(flo_ctx *ctx, const float *d_samples, size_t n_int
                               uint8_t channels, uint32_t peaks_per_second, float *d_peaks, size_t capacity, size_t *n_peaks);
 size_t flo_waveform_peaks_count(size_t n_interleaved, uint32_t sample_rate, uint8_t channels, uint32_t peaks_per_second);
 
+/* EBU R128 integrated loudness, the value libflo::encode() stores as loudness_profile[0].lufs (cast to f32).
+ * Replaces compute_ebu_r128_loudness(samples, channels, sample_rate).integrated_lufs
+ * (libflo/src/core/ebu_r128.rs:182-313, called from libflo/src/lib.rs:256-268): K-weighting per BS.1770
+ * (two biquads per channel), 400 ms blocks every 100 ms, -70 LUFS absolute and -10 LU relative gates.  The
+ * reference filters each channel as one serial f64 recurrence; the device filters its 100 ms hops in parallel and
+ * chains their states, so *lufs agrees with the reference to ~1e-12 LU, not bit for bit.  No samples,
+ * channels == 0 or no block above the absolute gate: -23.0, as in the reference.  loudness_range_lu, true_peak_dbtp
+ * and sample_peak_dbfs of LoudnessMetrics are not computed (encode() does not store them). */
+int flo_integrated_loudness(flo_ctx *ctx, const float *samples, size_t n_interleaved, uint32_t sample_rate,
+                            uint8_t channels, double *lufs);
+int flo_integrated_loudness_device(flo_ctx *ctx, const float *d_samples, size_t n_interleaved, uint32_t sample_rate,
+                                   uint8_t channels, double *lufs);
+
 /* Pinned host memory (optional).  Page-locked inputs go to the copy engine
  * directly; pageable inputs (a plain Rust slice) are staged by the library
  * through its own pinned ring with several copy threads (FLO_B200_COPY_THREADS

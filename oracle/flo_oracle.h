@@ -105,6 +105,11 @@ int      flo_ref_decode(const uint8_t *data, size_t len, float **out, size_t *ou
 /* same but stops before i32_to_f32: interleaved int32 (after M/S inverse) */
 int      flo_ref_decode_i32(const uint8_t *data, size_t len, int32_t **out, size_t *out_n);
 
+/* EBU R128 integrated loudness (flo_r128.c; libflo/src/core/ebu_r128.rs:58-102, 182-313) -- parity unpinned */
+void   flo_ref_kweighting_coeffs(double sample_rate, double out[10]);
+double flo_ref_r128_integrated(const float *samples, size_t n_interleaved, uint8_t channels, uint32_t sample_rate,
+                               double **block_energies_out, size_t *n_blocks);
+
 void        flo_ref_free(void *p);
 const char *flo_ref_last_error(void);
 

@@ -22,7 +22,7 @@ def build(force: bool = False) -> str:
     src = os.path.join(_HERE, "flo_oracle.c")
     hdr = os.path.join(_HERE, "flo_oracle.h")
     stale = (not os.path.exists(_SO)) or any(
-        os.path.exists(p) and os.path.getmtime(p) > os.path.getmtime(_SO) for p in (src, hdr, os.path.join(_HERE, "Makefile"))
+        os.path.exists(p) and os.path.getmtime(p) > os.path.getmtime(_SO) for p in (src, hdr, os.path.join(_HERE, "flo_r128.c"), os.path.join(_HERE, "Makefile"))
     )
     if force or stale:
         subprocess.check_call(["make", "-C", _HERE, "-s", "-B", "libflo_oracle.so"])
@@ -101,6 +101,10 @@ def lib() -> C.CDLL:
     L.flo_ref_decode_i32.argtypes = [C.c_void_p, C.c_size_t, C.POINTER(i32p), C.POINTER(C.c_size_t)]
     L.flo_ref_free.restype = None
     L.flo_ref_free.argtypes = [C.c_void_p]
+    L.flo_ref_kweighting_coeffs.restype = None
+    L.flo_ref_kweighting_coeffs.argtypes = [C.c_double, C.POINTER(C.c_double)]
+    L.flo_ref_r128_integrated.restype = C.c_double
+    L.flo_ref_r128_integrated.argtypes = [C.c_void_p, C.c_size_t, C.c_uint8, C.c_uint32, C.POINTER(C.POINTER(C.c_double)), C.POINTER(C.c_size_t)]
     L.flo_ref_last_error.restype = C.c_char_p
     L.flo_ref_last_error.argtypes = []
     _lib = L
@@ -438,6 +442,27 @@ class StreamingEncoderRef:
         out += toc + data + bytes(metadata)
         self.pending = []
         return out
+
+
+# ---- EBU R128 integrated loudness (ebu_r128.rs:182-313; flo_r128.c) -- parity unpinned ------------------------
+def kweighting_coeffs(sample_rate: float) -> List[float]:
+    out = (C.c_double * 10)()
+    lib().flo_ref_kweighting_coeffs(float(sample_rate), out)
+    return list(out)
+
+
+def r128_integrated_lufs(samples, channels: int, sample_rate: int, blocks: bool = False):
+    """compute_ebu_r128_loudness(samples, channels, sample_rate).integrated_lufs; with blocks=True also the 400 ms
+    block energies the gating runs over."""
+    x = np.ascontiguousarray(samples, dtype=np.float32).reshape(-1)
+    bp, nb = C.POINTER(C.c_double)(), C.c_size_t()
+    v = lib().flo_ref_r128_integrated(_ptr(x), x.size, channels, sample_rate, C.byref(bp) if blocks else None, C.byref(nb) if blocks else None)
+    if not blocks:
+        return float(v)
+    be = np.ctypeslib.as_array(bp, shape=(nb.value,)).copy() if nb.value else np.zeros(0)
+    if bp:
+        lib().flo_ref_free(C.cast(bp, C.c_void_p))
+    return float(v), be
 
 
 # ---- reflo's other ingest arms (reflo/src/audio.rs:255-269), numpy f32 arithmetic --------------------------

@@ -75,6 +75,10 @@ extern "C" {
                                      channels: u8, peaks_per_second: u32, d_peaks: *mut f32, capacity: usize,
                                      n_peaks: *mut usize) -> c_int;
     pub fn flo_waveform_peaks_count(n_interleaved: usize, sample_rate: u32, channels: u8, peaks_per_second: u32) -> usize;
+    pub fn flo_integrated_loudness(ctx: *mut flo_ctx, samples: *const f32, n_interleaved: usize, sample_rate: u32,
+                                   channels: u8, lufs: *mut f64) -> c_int;
+    pub fn flo_integrated_loudness_device(ctx: *mut flo_ctx, d_samples: *const f32, n_interleaved: usize, sample_rate: u32,
+                                          channels: u8, lufs: *mut f64) -> c_int;
     pub fn flo_decode(ctx: *mut flo_ctx, file: *const u8, len: usize, out: *mut *mut f32, n_interleaved: *mut usize,
                       info: *mut flo_info) -> c_int;
     pub fn flo_decode_device(ctx: *mut flo_ctx, d_file: *const c_void, len: usize, d_out: *mut f32,

@@ -4,7 +4,7 @@ oracle/flo_analysis.py)."""
 import numpy as np
 import pytest
 
-from helpers import pcm16_to_f32, synth_pcm16  # puts oracle/ on the path
+from helpers import oracle, pcm16_to_f32, synth_pcm16  # puts oracle/ on the path
 import flo_analysis  # noqa: E402  (oracle/: the checker)
 
 pytestmark = pytest.mark.gpu
@@ -82,3 +82,48 @@ def test_device_entry_on_ten_minutes(fa):
     assert same_bits(out.cpu().numpy(), want)
     with pytest.raises(Exception):
         fa.extract_waveform_peaks_device(x.data_ptr(), n, ch, sr, pps, out.data_ptr(), cap - 1)
+
+
+# ---- EBU R128 integrated loudness (libflo/src/core/ebu_r128.rs:182-313) ------------------------------------------
+LUFS_TOL = 1e-9      # LU; the device chains 100 ms hops instead of one serial recurrence per channel
+
+
+@pytest.mark.parametrize("ch,sr,secs,kind", [
+    (1, 44100, 3.0, "multitone"), (2, 44100, 5.3, "speech"), (2, 48000, 2.0, "sweep"), (1, 8000, 7.0, "speech"),
+    (6, 48000, 1.5, "multitone"), (2, 96000, 1.2, "sweep"), (1, 22050, 0.35, "multitone"), (2, 44100, 0.05, "multitone"),
+    (3, 12345, 2.2, "multitone"),
+])
+def test_integrated_loudness_matches_the_oracle(fa, ch, sr, secs, kind):
+    n = int(sr * secs)
+    x = pcm16_to_f32(synth_pcm16(n, ch, max(sr, 8000), seed=0xB00 + ch + sr, kind=kind, noise_lsb=32))
+    x = (x * np.float32(0.6)).astype(np.float32)
+    want = oracle.r128_integrated_lufs(x, ch, sr)
+    got = fa.compute_ebu_r128_loudness(x, ch, sr).integrated_lufs
+    assert abs(got - want) <= LUFS_TOL, (got, want)
+    assert np.float32(got) == np.float32(want)                                          # what encode() stores (lib.rs:262-265)
+    assert abs(fa.compute_ebu_r128_loudness(x[:-1], ch, sr).integrated_lufs - oracle.r128_integrated_lufs(x[:-1], ch, sr)) <= LUFS_TOL
+
+
+def test_loudness_corners_and_calibration(fa):
+    assert fa.compute_ebu_r128_loudness(np.zeros(0, np.float32), 1, 44100).integrated_lufs == -23.0      # loudness_tests.rs:4-12
+    assert fa.compute_ebu_r128_loudness(np.zeros(44100, np.float32), 1, 44100).integrated_lufs == -23.0  # :15-23
+    assert fa.compute_ebu_r128_loudness(np.ones(10, np.float32), 0, 44100).integrated_lufs == -23.0      # ebu_r128.rs:187
+    assert fa.compute_ebu_r128_loudness(np.ones(1, np.float32), 2, 44100).integrated_lufs == -23.0       # no whole frame
+    sr = 48000
+    s997 = np.sin(2 * np.pi * 997 * np.arange(sr * 5) / sr).astype(np.float32)
+    assert abs(fa.compute_ebu_r128_loudness(s997, 1, sr).integrated_lufs - (-3.01)) < 0.01               # BS.1770 calibration
+    loud = (0.5 * np.sin(2 * np.pi * 440 * np.arange(44100 * 4) / 44100)).astype(np.float32)
+    both = np.concatenate([loud, loud * np.float32(10 ** -1.5), np.zeros(44100, np.float32)])           # both gates at work
+    assert abs(fa.compute_ebu_r128_loudness(both, 1, 44100).integrated_lufs - oracle.r128_integrated_lufs(both, 1, 44100)) <= LUFS_TOL
+
+
+def test_loudness_device_entry_on_ten_minutes(fa):
+    import torch
+    sr, ch = 44100, 2
+    n = sr * ch * 600
+    dev = torch.device("cuda", 0)
+    g = torch.Generator(device=dev).manual_seed(11)
+    x = (torch.rand(n, device=dev, generator=g) - 0.5) * (0.05 + 0.5 * torch.sin(torch.linspace(0, 40, n, device=dev)) ** 2)
+    got = fa.integrated_loudness_device(x.data_ptr(), n, ch, sr)
+    want = oracle.r128_integrated_lufs(x.cpu().numpy(), ch, sr)
+    assert abs(got - want) <= LUFS_TOL, (got, want)

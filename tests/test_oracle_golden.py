@@ -257,3 +257,41 @@ def test_waveform_peaks_hand_derived_unpinned():
     assert flo_analysis.extract_waveform_peaks([nan, 0.5, nan, nan], 1, 2, 1).tolist() == [1.0, 0.0]  # f32::max skips NaN
     with pytest.raises(OverflowError):
         flo_analysis.extract_waveform_peaks([1.0], 0, 44100, 10)
+
+
+# ---- EBU R128 integrated loudness (libflo/src/core/ebu_r128.rs): PARITY UNPINNED against the reference (its tests
+# assert ranges only, libflo/tests/rust/loudness_tests.rs); pinned against the standard it implements instead
+def test_r128_kweighting_is_bs1770_at_48k():
+    """ITU-R BS.1770 publishes the two K-weighting biquads at 48 kHz; KWeighting::new (ebu_r128.rs:58-102) derives
+    them from the analogue prototype and must land on the table."""
+    co = oracle.kweighting_coeffs(48000.0)
+    shelf = [1.53512485958697, -2.69169618940638, 1.19839281085285, -1.69065929318241, 0.73248077421585]
+    hp_a = [-1.99004745483398, 0.99007225036621]
+    assert np.allclose(co[:5], shelf, rtol=0, atol=1e-13)
+    assert co[5:8] == [1.0, -2.0, 1.0] and np.allclose(co[8:], hp_a, rtol=0, atol=1e-13)
+
+
+def test_r128_calibration_and_reference_ranges_unpinned():
+    sr = 48000
+    t = np.arange(sr * 5)
+    full_scale_997 = np.sin(2 * np.pi * 997 * t / sr).astype(np.float32)
+    assert abs(oracle.r128_integrated_lufs(full_scale_997, 1, sr) - (-3.01)) < 0.01      # BS.1770 calibration point
+    assert oracle.r128_integrated_lufs(np.zeros(0, np.float32), 1, 44100) == -23.0        # loudness_tests.rs:4-12
+    assert oracle.r128_integrated_lufs(np.zeros(44100, np.float32), 1, 44100) == -23.0    # :15-23
+    f = np.float32
+    for sr in (22050, 44100, 48000, 96000):                                               # :26-41, :83-97
+        i = np.arange(sr, dtype=np.float32)
+        x = (f(0.5) * np.sin(f(2.0) * f(np.pi) * f(440.0) * i / f(sr))).astype(np.float32)
+        assert -25.0 < oracle.r128_integrated_lufs(x, 1, sr) < -5.0
+    for ch in (1, 2, 4, 6):                                                               # :100-117
+        i = np.arange(44100, dtype=np.float32)
+        s = (f(0.3) * np.sin(f(2.0) * f(np.pi) * f(440.0) * i / f(44100))).astype(np.float32)
+        assert -35.0 < oracle.r128_integrated_lufs(np.repeat(s, ch), ch, 44100) < -5.0
+    i = np.arange(44100 * 2, dtype=np.uint64)                                             # :62-80 white noise
+    seed = (i * np.uint64(1103515245) + np.uint64(12345)) & np.uint64(0x7fffffff)
+    noise = (0.1 * (seed.astype(np.float64) / 2147483647.0 - 0.5) * 2.0).astype(np.float32)
+    assert -40.0 < oracle.r128_integrated_lufs(noise, 1, 44100) < -10.0
+    # the relative gate: a loud half and a 30 dB quieter half read (nearly) as the loud half alone
+    loud = (0.5 * np.sin(2 * np.pi * 440 * np.arange(44100 * 4) / 44100)).astype(np.float32)
+    both = np.concatenate([loud, loud * np.float32(10 ** -1.5)])
+    assert abs(oracle.r128_integrated_lufs(both, 1, 44100) - oracle.r128_integrated_lufs(loud, 1, 44100)) < 0.2
