@@ -633,6 +633,20 @@ static int encode_batch_impl(flo_ctx *c, const flo_track *tracks, size_t n_track
     if (n_waves < 1) n_waves = 1;
     std::vector<uint32_t> wave_end(n_waves);
     for (int w = 0; w < n_waves; w++) wave_end[w] = (uint32_t)((uint64_t)NF * (w + 1) / n_waves);
+    // The call ends one wave's encode and one wave's D2H after the last H2D: the last wave is halved again and again
+    // (down to about half a frame per CTA) so that this tail is short -- its pieces are still uploaded back to back.
+    // 1-hour stereo stream, 4 waves of 900 frames: tail 2.3 ms -> 0.7 ms of a 26.8 ms call.
+    if (n_waves > 1 && !getenv("FLO_B200_NO_TAPER")) {
+        uint32_t begin = wave_end[n_waves - 2], rest = NF - begin;
+        wave_end.pop_back();
+        while (rest > (uint32_t)grid / 2u + 1u && (int)wave_end.size() < MAX_WAVES - 1) {
+            const uint32_t piece = (rest + 1u) / 2u;
+            begin += piece; rest -= piece;
+            wave_end.push_back(begin);
+        }
+        if (rest) wave_end.push_back(NF);
+        n_waves = (int)wave_end.size();
+    }
     const bool piped = n_waves > 1;
     cudaStream_t s_in = piped ? c->s_in : st;
 
