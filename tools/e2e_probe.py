@@ -1,5 +1,5 @@
 """Where an end-to-end host call spends its time: wall time of flo_encode_batch (pinned host f32 in, pinned .flo out)
-next to the library's own event timings.  usage: python tools/e2e_probe.py [seconds=3600]"""
+next to the library's own event timings.  usage: python tools/e2e_probe.py [seconds=3600] [pageable]"""
 import os, sys, time
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "tools"))
@@ -8,7 +8,8 @@ SR, CH = 44100, 2
 secs = int(sys.argv[1]) if len(sys.argv) > 1 else 3600
 pcm = synth_torch.synth_pcm16_long(secs * SR, CH, SR, 0xF12, "multitone", 64, "cuda")
 x = (pcm.float() * (1 / 32768))
-h = torch.empty(x.numel(), dtype=torch.float32, pin_memory=True); h.copy_(x); torch.cuda.synchronize()
+pageable = len(sys.argv) > 2 and sys.argv[2] == "pageable"
+h = torch.empty(x.numel(), dtype=torch.float32, pin_memory=not pageable); h.copy_(x); torch.cuda.synchronize()
 ctx = flo_b200.Context(0)
 specs = [flo_b200.TrackSpec(h.numpy(), SR, CH, 16, b"")]
 for i in range(5):
