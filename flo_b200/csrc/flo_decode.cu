@@ -243,6 +243,33 @@ __device__ __forceinline__ uint32_t rice_try(uint32_t rs, BitIn &b, uint32_t k, 
     b.nb -= take;
     return u;
 }
+// The same step for the group transaction of the bit-reading warp, which rolls the reader back when any code of the
+// group failed: nothing has to be preserved on failure, so the step is shorter.  After the append the window holds
+// more than 32 bits, so a code of at most 32 bits (run <= 31 - k, one unsigned compare that also catches the all-ones
+// word) always fits and lies entirely in the top word; window and bit count advance unconditionally (garbage after a
+// failure, never an unsafe access: shifts clamp, the ring index is masked).
+struct RiceK { uint32_t k, kp1, lim, pk; };               // k, k + 1, 31 - k, 2^k
+__device__ __forceinline__ uint32_t rice_step(uint32_t rs, uint32_t &hi, uint32_t &lo, int &nb, uint32_t &rd, uint32_t &nxt,
+                                              const RiceK &K, bool &all_ok) {
+    if (nb <= 32) {
+        const uint32_t w = be(nxt);
+        hi |= __funnelshift_rc(w, 0u, (uint32_t)nb);
+        lo = __funnelshift_lc(0u, w, 32u - (uint32_t)nb);
+        nb += 32;
+        rd++;
+    }
+    nxt = ring_at(rs, rd);
+    uint32_t run;
+    asm("bfind.shiftamt.u32 %0, %1;" : "=r"(run) : "r"(~hi));
+    all_ok = all_ok && run <= K.lim;
+    const uint32_t used = run + K.kp1;
+    const uint32_t t = __funnelshift_lc(0u, hi, run + 1u);                 // hi << (run + 1)
+    const uint32_t u = run * K.pk + __funnelshift_rc(t, 0u, 32u - K.k);    // remainder < 2^k: add = or
+    hi = __funnelshift_lc(lo, hi, used);
+    lo = __funnelshift_lc(0u, lo, used);
+    nb -= (int)used;
+    return u;
+}
 __device__ __forceinline__ uint32_t rice_next_u(uint32_t rs, BitIn &b, uint32_t k) {
     bool ok;
     uint32_t u = rice_try(rs, b, k, ok);
@@ -382,6 +409,7 @@ __device__ __forceinline__ void consumer_loop(const Lane &L, uint32_t res0, uint
 }
 // Bit-reading warp: residual i of every lane, as its zigzag code -> res[block parity][i % BLK][lane].
 __device__ __forceinline__ void producer_loop(Lane &L, uint32_t res0, uint32_t nblk, bool any_pcm) {
+    const RiceK K = {L.k, L.k + 1u, 31u - L.k, 1u << L.k};           // k <= 31 (lane_setup)
     for (uint32_t ph = 0; ph <= nblk; ph++) {
         if (ph < nblk) {
             const uint32_t res = res0 + ((ph & 1u) ? 128u * BLK : 0u);
@@ -397,13 +425,16 @@ __device__ __forceinline__ void producer_loop(Lane &L, uint32_t res0, uint32_t n
                     const uint32_t rd0 = b.rd, nxt0 = b.nxt;
                     uint32_t u[GROUP];
                     bool all_ok = true;
+                    uint32_t hi = (uint32_t)(buf0 >> 32), lo = (uint32_t)buf0, rd = rd0, nxt = nxt0;
+                    int nb = nb0;
                     #pragma unroll
-                    for (int t = 0; t < GROUP; t++) { bool ok; u[t] = rice_try(L.rs, b, L.k, ok); all_ok = all_ok && ok; }
+                    for (int t = 0; t < GROUP; t++) u[t] = rice_step(L.rs, hi, lo, nb, rd, nxt, K, all_ok);
                     if (__builtin_expect(!all_ok, 0)) {
                         b.buf = buf0; b.nb = nb0; b.rd = rd0; b.nxt = nxt0;
                         #pragma unroll 1
                         for (int t = 0; t < GROUP; t++) sts32(res + 128u * (g + t), rice_next_u(L.rs, b, L.k));
                     } else {
+                        b.buf = ((unsigned long long)hi << 32) | lo; b.nb = nb; b.rd = rd; b.nxt = nxt;
                         #pragma unroll
                         for (int t = 0; t < GROUP; t++) sts32(res + 128u * (g + t), u[t]);
                     }
