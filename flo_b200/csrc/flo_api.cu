@@ -1167,6 +1167,16 @@ int loudness_impl(flo_ctx *c, const float *h_x, const float *d_x, size_t n, uint
     flo::KwParams kp;
     kp.x = d_x; kp.frames = frames; kp.channels = ch; kp.hop = hop; kp.n_hops = n_hops;
     kweighting_coeffs(srd, kp.co);
+    // Below ~3.4 kHz the shelf's corner (1682 Hz) lies above Nyquist and the prototype yields an UNSTABLE biquad
+    // (|a2| > 1): the reference's output there is an overflow to inf.  Hop states cannot be chained through an
+    // unstable filter, and inf is not a loudness: refused.
+    for (int q = 0; q < 2; q++) {
+        const double a1 = kp.co[5 * q + 3], a2 = kp.co[5 * q + 4];
+        if (!(std::fabs(a2) < 1.0 && std::fabs(a1) < 1.0 + a2)) {
+            set_err("loudness: the K-weighting filter is unstable at %u Hz (the reference overflows to inf)", sr);
+            return FLO_ERR_ARG;
+        }
+    }
     kp.state = (double *)c->peaks.p;
     kp.hop_sum = kp.state + 4 * n_seg;
     std::vector<double> hs(n_seg * 4);

@@ -196,7 +196,8 @@ size_t flo_waveform_peaks_count(size_t n_interleaved, uint32_t sample_rate, uint
  * (two biquads per channel), 400 ms blocks every 100 ms, -70 LUFS absolute and -10 LU relative gates.  The
  * reference filters each channel as one serial f64 recurrence; the device filters its 100 ms hops in parallel and
  * chains their states, so *lufs agrees with the reference to ~1e-12 LU, not bit for bit.  No samples,
- * channels == 0 or no block above the absolute gate: -23.0, as in the reference.  loudness_range_lu, true_peak_dbtp
+ * channels == 0 or no block above the absolute gate: -23.0, as in the reference.  Sample rates below ~3.4 kHz,
+ * where the reference's shelf filter is unstable and its result overflows to inf, are refused (FLO_ERR_ARG).  loudness_range_lu, true_peak_dbtp
  * and sample_peak_dbfs of LoudnessMetrics are not computed (encode() does not store them). */
 int flo_integrated_loudness(flo_ctx *ctx, const float *samples, size_t n_interleaved, uint32_t sample_rate,
                             uint8_t channels, double *lufs);

@@ -109,6 +109,11 @@ def test_loudness_corners_and_calibration(fa):
     assert fa.compute_ebu_r128_loudness(np.zeros(44100, np.float32), 1, 44100).integrated_lufs == -23.0  # :15-23
     assert fa.compute_ebu_r128_loudness(np.ones(10, np.float32), 0, 44100).integrated_lufs == -23.0      # ebu_r128.rs:187
     assert fa.compute_ebu_r128_loudness(np.ones(1, np.float32), 2, 44100).integrated_lufs == -23.0       # no whole frame
+    import flo_b200
+    x1k = pcm16_to_f32(synth_pcm16(3000, 1, 8000, seed=3))
+    assert oracle.r128_integrated_lufs(x1k, 1, 1000) == float("inf")                   # unstable shelf below ~3.4 kHz: overflow
+    with pytest.raises(flo_b200.FloError):
+        fa.compute_ebu_r128_loudness(x1k, 1, 1000)
     sr = 48000
     s997 = np.sin(2 * np.pi * 997 * np.arange(sr * 5) / sr).astype(np.float32)
     assert abs(fa.compute_ebu_r128_loudness(s997, 1, sr).integrated_lufs - (-3.01)) < 0.01               # BS.1770 calibration

@@ -20,4 +20,21 @@ for variant in (None, "512", "256", "128"):
         x = pcm16_to_f32(pcm)
         got = flo_b200.Encoder(sr, ch, 16, context=ctx).with_compression(lvl).encode(x, b"m")
         assert got == oracle.encode(x, sr, ch, 16, lvl, b"m"), (variant, n, ch, sr, lvl)
+os.environ.pop("FLO_B200_VARIANT", None)
+# decoder, analysis entries (round 2): decode round trip, waveform peaks, R128 loudness incl. ragged and many-channel inputs
+from flo_b200 import analysis as fa
+sys.path.insert(0, os.path.join(ROOT, "oracle"))
+import flo_analysis
+for n, ch, sr, lvl in cases:
+    x = pcm16_to_f32(synth_pcm16(n, ch, sr, seed=n + ch))
+    img = flo_b200.Encoder(sr, ch, 16, context=ctx).with_compression(lvl).encode(x, b"")
+    dec = flo_b200.Decoder().decode(img)
+    assert np.array_equal(dec, oracle.decode(img))
+    pk = fa.extract_waveform_peaks(x, ch, sr, 50, ctx=ctx).peaks
+    assert np.array_equal(pk.view(np.uint32), flo_analysis.extract_waveform_peaks(x, ch, sr, 50).view(np.uint32))
+    if sr >= 8000:                                                  # below ~3.4 kHz the reference's shelf filter is unstable
+        lu = fa.compute_ebu_r128_loudness(x, ch, sr, ctx=ctx).integrated_lufs
+        assert abs(lu - oracle.r128_integrated_lufs(x, ch, sr)) < 1e-9
+x = pcm16_to_f32(synth_pcm16(9 * 5000 + 3, 9, 8000, seed=5))        # more than 8 channels: the unstaged K-weighting kernel
+assert abs(fa.compute_ebu_r128_loudness(x, 9, 8000, ctx=ctx).integrated_lufs - oracle.r128_integrated_lufs(x, 9, 8000)) < 1e-9
 print("sanitize_case ok")
