@@ -1,8 +1,9 @@
-"""Small mixed workload for compute-sanitizer (memcheck / racecheck): every kernel variant, both plane
+"""(Test infrastructure, run by hand on a GPU box: `python tests/sanitize_case.py`, optionally under compute-sanitizer.)
+Small mixed workload for compute-sanitizer (memcheck / racecheck): every kernel variant, both plane
 placements, levels 2/5/9, mono / stereo / 3 channels, ragged tails; results are checked against the oracle."""
 import os, sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "tests"))
+sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "tests")); sys.path.insert(0, os.path.join(ROOT, "tools"))
 import numpy as np
 from helpers import oracle, pcm16_to_f32, synth_pcm16
 import flo_b200

@@ -1,9 +1,8 @@
 """Timing of the analysis-metadata entries (row N4) on one hour of 44.1 kHz stereo f32 resident in HBM:
-waveform peaks (50 per second) and EBU R128 integrated loudness; the loudness is also compared with the CPU oracle
-on the first 10 minutes (checker only).  usage: python tools/bench_analysis.py [seconds=3600]"""
+waveform peaks (50 per second) and EBU R128 integrated loudness (parity with the oracle: tests/test_gpu_analysis.py).  usage: python tools/bench_analysis.py [seconds=3600]"""
 import json, os, sys, time
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "tools")); sys.path.insert(0, os.path.join(ROOT, "oracle"))
+sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "tools"))
 import torch, flo_b200, synth_torch
 from flo_b200 import analysis as fa
 SR, CH = 44100, 2
@@ -25,9 +24,4 @@ def loud(): lufs[0] = fa.integrated_loudness_device(x.data_ptr(), n, CH, SR)
 t_loud = timed(loud)
 out = {"audio_seconds": secs, "input_GB": n * 4 / 1e9, "peaks_ms": t_peaks, "peaks_GBps": n * 4 / t_peaks / 1e6, "n_peaks": cap,
        "loudness_ms": t_loud, "loudness_GBps_per_pass": n * 4 / t_loud / 1e6, "integrated_lufs": lufs[0]}
-import flo_oracle
-m = min(n, SR * CH * 600)
-t0 = time.perf_counter(); want = flo_oracle.r128_integrated_lufs(x[:m].cpu().numpy(), CH, SR); cpu_ms = (time.perf_counter() - t0) * 1e3
-got = fa.integrated_loudness_device(x.data_ptr(), m, CH, SR)
-out.update({"oracle_lufs_first_600s": want, "device_lufs_first_600s": got, "abs_diff_LU": abs(got - want), "oracle_cpu_ms_600s": cpu_ms})
 print(json.dumps(out))
