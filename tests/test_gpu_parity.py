@@ -446,3 +446,27 @@ def test_s32_device_entry_and_batch():
     for i, n in enumerate([pcm.size, pcm.size // 2]):
         got = host[int(offs[i]):int(offs[i]) + int(lens[i])].tobytes()
         assert got == oracle.encode(oracle.s32_to_f32(pcm[:n]), sr, ch, 16, 5, b"")
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("knob,value", [("FLO_B200_VARIANT", "512"), ("FLO_B200_VARIANT", "256"), ("FLO_B200_VARIANT", "128"),
+                                        ("FLO_B200_DEFER_KB", "0"), ("FLO_B200_DEFER_KB", "512")])
+def test_every_kernel_variant_and_pack_placement(fb, ctx, knob, value):
+    """The host picks the kernel build (512 x 1, 256 x 2 or 3, 128 x 4 CTAs per SM) and the pack placement (in place, or
+    a per-CTA scratch for frames up to 48 KB) from the batch; here every build and both placements are forced
+    (the knobs are read per call) over inputs of every shape, so none of them is only covered when the planner
+    happens to choose it."""
+    import os
+    old = os.environ.get(knob)
+    os.environ[knob] = value
+    try:
+        for n, ch, sr, kind, noise in CASES:
+            x = pcm16_to_f32(synth_pcm16(min(n, sr + sr // 2 + 3), ch, sr, seed=0xE0 + ch + sr, kind=kind, noise_lsb=noise))
+            for level in (2, 5, 8):
+                got = fb.Encoder(sr, ch, 16, context=ctx).with_compression(level).encode(x, b"v")
+                assert got == oracle.encode(x, sr, ch, 16, level, b"v"), (knob, value, sr, ch, kind, level)
+    finally:
+        if old is None:
+            os.environ.pop(knob, None)
+        else:
+            os.environ[knob] = old
