@@ -22,6 +22,9 @@ constexpr int NWARP = NT / 32;
 #ifndef FLO_SINGLE_BS
 #define FLO_SINGLE_BS 4       // samples per block of a one-order FIR sweep (independent chains)
 #endif
+#ifndef FLO_PACK_BS
+#define FLO_PACK_BS 4         // independent FIR chains of the packer's (and pass 3's) residual recomputation (8: no change, 3.06 ms)
+#endif
 #ifndef FLO_PAIR_SWEEPS
 #define FLO_PAIR_SWEEPS 0     // 1: two LPC orders per sweep share one window (fewer loads, but the second set of chains and
 #endif                        //    coefficients spills ~1.5 KB per thread at 128 registers: 3.13 vs 3.08 ms at level 5)
@@ -749,7 +752,7 @@ __device__ __forceinline__ void cand_chunk(const i32 (&x)[NHX + CH], const doubl
         fixed_chunk<MODE + 1, FIRST>(x + (NHX - 4), [&](int j, const i32 (&d)[5]) { fn(j, d[MODE]); });
     } else {
         static_assert(NHX >= MODE, "history");
-        lpc_chunk2<NHX, MODE, 0, 4, FIRST>(x, qd, qd, fn, [](int, i32) {});
+        lpc_chunk2<NHX, MODE, 0, FLO_PACK_BS, FIRST>(x, qd, qd, fn, [](int, i32) {});
     }
 }
 
