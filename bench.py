@@ -78,6 +78,8 @@ class ClockSampler:
         self.index, self.rows, self.proc = index, [], None
 
     def start(self):
+        if os.environ.get("FLO_BENCH_NO_CLOCKS"):      # diagnosis only: a line without clocks is not a valid bench line
+            return
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}",
                                           "--format=csv,noheader,nounits", "-lms", "20"],
@@ -304,17 +306,25 @@ def main() -> int:
     d_out = torch.empty(bound, dtype=torch.uint8, device=dev)
     ptrs = [t.data_ptr() for t in f32_tracks]
 
+    # The exchange of a step is issued by a helper thread while the main thread is already inside the next encode call
+    # (ctypes releases the GIL for the call's 3 ms): its ~0.2 ms of tensor set-up and NCCL launch no longer leave the GPU
+    # idle between steps.  One helper, so every rank issues its all_gathers in step order.
+    xpool = None
+    if world > 1:
+        from concurrent.futures import ThreadPoolExecutor
+        xpool = ThreadPoolExecutor(max_workers=1, initializer=lambda: torch.cuda.set_device(dev))
+
     def step():
         off, ln = ctx.encode_batch_device(ptrs, n_list, [SR] * nt, [CH] * nt, [BITS] * nt, d_out.data_ptr(), bound, level=level)
         if world > 1:       # per-track byte lengths for the final concatenation (the only exchange), non-blocking
-            pending.append(shard.exchange_lengths_async([int(v) for v in ln], ranges))
+            pending.append(xpool.submit(shard.exchange_lengths_async, [int(v) for v in ln], ranges))
         return off, ln
 
     pending = []
 
     def sync_all():
         while pending:      # the concatenation offsets of every step are complete before the clock stops
-            pending.pop().result()
+            pending.pop().result().result()
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
@@ -568,6 +578,8 @@ def main() -> int:
             print("bench.py: the timed output differs from the CPU oracle: " + json.dumps(parity), file=sys.stderr)
             rc = 3
     if world > 1:
+        if xpool is not None:
+            xpool.shutdown()
         dist.destroy_process_group()
     return rc
 
