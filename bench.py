@@ -441,6 +441,27 @@ def main() -> int:
                             "pct_of_hbm_peak": 100.0 * (4.0 * total_inter + float(l2[0])) / (k_dec * 1e-3) / 1e9 / peak}
         del d_dec, q
 
+        # companion row N4: the analysis metadata libflo::encode() attaches, on the same resident f32 stream (wall time of
+        # the C-ABI call incl. its synchronisation; parity with the oracle: tests/test_gpu_analysis.py)
+        from flo_b200 import analysis as fa
+        cap = fa.peaks_count(total_inter, SR, CH, 50)
+        d_peaks = torch.empty(max(cap, 1), dtype=torch.float32, device=dev)
+        x0 = f32_tracks[0]
+
+        def best_ms(f, reps=3):
+            f(); torch.cuda.synchronize()
+            best = None
+            for _ in range(reps):
+                t0 = time.perf_counter(); f(); torch.cuda.synchronize()
+                best = min(best, time.perf_counter() - t0) if best is not None else time.perf_counter() - t0
+            return best * 1e3
+        lufs_box = [None]
+        pk_ms = best_ms(lambda: fa.extract_waveform_peaks_device(x0.data_ptr(), x0.numel(), CH, SR, 50, d_peaks.data_ptr(), cap, ctx=ctx))
+        lu_ms = best_ms(lambda: lufs_box.__setitem__(0, fa.integrated_loudness_device(x0.data_ptr(), x0.numel(), CH, SR, ctx=ctx)))
+        extras["analysis"] = {"waveform_peaks": {"peaks": cap, "call_ms": pk_ms, "pct_of_hbm_peak": 100.0 * 4.0 * x0.numel() / (pk_ms * 1e-3) / 1e9 / peak},
+                              "r128_integrated_loudness": {"lufs": lufs_box[0], "call_ms": lu_ms, "passes_over_the_input": 2}}
+        del d_peaks
+
         # the other BASELINE configs, device-resident (their own bench lines: bench.py --config 3|4|5)
         extras["configs"] = {}
         for cid, kw in ((3, dict(tracks=20)), (4, dict(seconds=1184)), (5, dict())):
