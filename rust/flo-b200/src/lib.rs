@@ -161,3 +161,24 @@ impl Decoder {
         Ok(v)
     }
 }
+
+/// `core::analysis::extract_waveform_peaks` (libflo/src/core/analysis.rs:38-119): the normalised peaks of
+/// `WaveformData`, bit-identical to the reference.  Same argument order as the reference.
+pub fn extract_waveform_peaks(ctx: &Arc<Context>, samples: &[f32], channels: u8, sample_rate: u32, peaks_per_second: u32) -> FloResult<Vec<f32>> {
+    let (mut out, mut n) = (ptr::null_mut::<f32>(), 0usize);
+    let rc = unsafe { ffi::flo_waveform_peaks(ctx.0, samples.as_ptr(), samples.len(), sample_rate, channels, peaks_per_second, &mut out, &mut n) };
+    if rc != 0 { return Err(last_error()); }
+    if out.is_null() { return Ok(Vec::new()); }
+    let v = unsafe { std::slice::from_raw_parts(out, n).to_vec() };
+    unsafe { ffi::flo_free(out as *mut _) };
+    Ok(v)
+}
+
+/// `core::ebu_r128::compute_ebu_r128_loudness(..).integrated_lufs` (libflo/src/core/ebu_r128.rs:182-313), the value
+/// `libflo::encode()` stores as `loudness_profile[0].lufs`; agrees with the reference to ~1e-12 LU (see the header).
+pub fn integrated_loudness(ctx: &Arc<Context>, samples: &[f32], channels: u8, sample_rate: u32) -> FloResult<f64> {
+    let mut lufs = 0f64;
+    let rc = unsafe { ffi::flo_integrated_loudness(ctx.0, samples.as_ptr(), samples.len(), sample_rate, channels, &mut lufs) };
+    if rc != 0 { return Err(last_error()); }
+    Ok(lufs)
+}
