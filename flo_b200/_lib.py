@@ -43,7 +43,7 @@ EXPORTS = [
     "flo_ctx_last_counters", "flo_ctx_enable_report", "flo_ctx_read_report", "flo_host_alloc", "flo_host_free", "flo_free",
     "flo_last_error", "flo_version", "flo_device_count", "flo_decode", "flo_decode_device", "flo_stream_encode_frames",
     "flo_waveform_peaks", "flo_waveform_peaks_device", "flo_waveform_peaks_count",
-    "flo_integrated_loudness", "flo_integrated_loudness_device",
+    "flo_integrated_loudness", "flo_integrated_loudness_device", "flo_decode_i16", "flo_decode_i16_device",
 ]
 
 _lib = None
@@ -87,6 +87,10 @@ def lib() -> C.CDLL:
     L.flo_decode.argtypes = [vp, vp, sz, C.POINTER(vp), C.POINTER(sz), C.POINTER(Info)]
     L.flo_decode_device.restype = C.c_int
     L.flo_decode_device.argtypes = [vp, vp, sz, vp, sz, C.POINTER(sz), C.POINTER(Info)]
+    L.flo_decode_i16.restype = C.c_int
+    L.flo_decode_i16.argtypes = [vp, vp, sz, C.POINTER(vp), C.POINTER(sz), C.POINTER(Info)]
+    L.flo_decode_i16_device.restype = C.c_int
+    L.flo_decode_i16_device.argtypes = [vp, vp, sz, vp, sz, C.POINTER(sz), C.POINTER(Info)]
     L.flo_stream_encode_frames.restype = C.c_int
     L.flo_stream_encode_frames.argtypes = [vp, vp, sz, u32, u8, u8, u8, C.POINTER(vp), C.POINTER(sz), C.POINTER(vp), C.POINTER(u32)]
     L.flo_waveform_peaks.restype = C.c_int

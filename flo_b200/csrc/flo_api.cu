@@ -1290,8 +1290,10 @@ int decode_error(uint32_t key) {
     return FLO_ERR_ARG;
 }
 
-int decode_impl(flo_ctx *c, const uint8_t *h_file, const void *d_file, size_t len, float *d_out_user, size_t cap,
-                float **out, size_t *n_out, flo_info *info) {
+// i16: 0 = interleaved f32 (the reference's result), 1 = the integer samples saturated to i16 (flo_decode_i16)
+int decode_impl(flo_ctx *c, const uint8_t *h_file, const void *d_file, size_t len, void *d_out_user, size_t cap,
+                void **out, size_t *n_out, flo_info *info, int i16) {
+    const size_t esz = i16 ? sizeof(int16_t) : sizeof(float);
     if (!c || !n_out || (!h_file && !d_file) || (h_file && !out)) { set_err("bad argument"); return FLO_ERR_ARG; }
     *n_out = 0;
     if (out) *out = nullptr;
@@ -1329,7 +1331,7 @@ int decode_impl(flo_ctx *c, const uint8_t *h_file, const void *d_file, size_t le
     p.file = df; p.len = len; p.toc_pos = H.toc_pos; p.n_toc = H.n_toc; p.channels = C;
     p.data_start = H.data_start; p.data_end = H.data_end;
     p.frames = (flo::DecFrame *)c->dec_frames.p; p.units = (flo::DecUnit *)c->dec_units.p;
-    p.base = (unsigned long long *)c->dec_base.p; p.ctl = (uint32_t *)c->dec_ctl.p; p.out = nullptr;
+    p.base = (unsigned long long *)c->dec_base.p; p.ctl = (uint32_t *)c->dec_ctl.p; p.out = nullptr; p.out_i16 = i16;
     CK(flo::launch_decode_parse(p, st));
     CK(cudaEventRecord(c->ev[2], st));
     CK(cudaMemcpyAsync(hc + 8, c->dec_ctl.p, 16, cudaMemcpyDeviceToHost, st));
@@ -1340,15 +1342,15 @@ int decode_impl(flo_ctx *c, const uint8_t *h_file, const void *d_file, size_t le
     const uint64_t n = total * C;
     *n_out = (size_t)n;
 
-    float *d_out = d_out_user;
+    void *d_out = d_out_user;
     if (h_file) {
-        if (int rc = c->out.reserve(n * sizeof(float) + 64)) return rc;
-        d_out = (float *)c->out.p;
+        if (int rc = c->out.reserve(n * esz + 64)) return rc;
+        d_out = c->out.p;
     } else if (n > cap || (n && !d_out_user)) {
-        set_err("flo_decode_device: output capacity %zu floats, %llu needed", cap, (unsigned long long)n);
+        set_err("flo_decode_device: output capacity %zu samples, %llu needed", cap, (unsigned long long)n);
         return FLO_ERR_ARG;
     }
-    p.out = d_out;
+    p.out = d_out; p.out_i16 = i16;
     p.n_toc = keep;
     CK(cudaEventRecord(c->ev[3], st));
     uint32_t launches = H.n_toc ? 2 : 1;
@@ -1357,19 +1359,19 @@ int decode_impl(flo_ctx *c, const uint8_t *h_file, const void *d_file, size_t le
     CK(cudaMemcpyAsync(hc + 8, c->dec_ctl.p, 16, cudaMemcpyDeviceToHost, st));
 
     OutBlock *blk = nullptr;
-    float *h_out = nullptr;
+    void *h_out = nullptr;
     struct Guard {                                         // releases the result buffer on every early return
-        OutBlock *&blk; float *&h_out; cudaStream_t st; bool armed = true;
+        OutBlock *&blk; void *&h_out; cudaStream_t st; bool armed = true;
         ~Guard() { if (!armed) return; cudaStreamSynchronize(st); cudaGetLastError(); if (blk) drop_block(blk); else free(h_out); }
     } guard{blk, h_out, st};
     if (h_file) {
-        const size_t bytes = (size_t)n * sizeof(float);
+        const size_t bytes = (size_t)n * esz;
         if (bytes >= SMALL_OUTPUT) {
             blk = take_block(bytes);
             if (!blk) { set_err("pinned output allocation (%zu bytes) failed", bytes); return FLO_ERR_NOMEM; }
-            h_out = (float *)blk->base;
+            h_out = blk->base;
         } else {
-            h_out = (float *)malloc(bytes ? bytes : 1);
+            h_out = malloc(bytes ? bytes : 1);
             if (!h_out) { set_err("malloc(%zu) failed", bytes); return FLO_ERR_NOMEM; }
         }
         if (bytes) CK(cudaMemcpyAsync(h_out, d_out, bytes, cudaMemcpyDeviceToHost, st));
@@ -1409,10 +1411,19 @@ int decode_impl(flo_ctx *c, const uint8_t *h_file, const void *d_file, size_t le
 
 extern "C" int flo_decode(flo_ctx *c, const uint8_t *file, size_t len, float **out, size_t *n_interleaved, flo_info *info) {
     if (!file) { set_err("bad argument"); return FLO_ERR_ARG; }
-    return decode_impl(c, file, nullptr, len, nullptr, 0, out, n_interleaved, info);
+    return decode_impl(c, file, nullptr, len, nullptr, 0, (void **)out, n_interleaved, info, 0);
 }
 extern "C" int flo_decode_device(flo_ctx *c, const void *d_file, size_t len, float *d_out, size_t d_out_capacity,
                                  size_t *n_interleaved, flo_info *info) {
     if (!d_file) { set_err("bad argument"); return FLO_ERR_ARG; }
-    return decode_impl(c, nullptr, d_file, len, d_out, d_out_capacity, nullptr, n_interleaved, info);
+    return decode_impl(c, nullptr, d_file, len, d_out, d_out_capacity, nullptr, n_interleaved, info, 0);
+}
+extern "C" int flo_decode_i16(flo_ctx *c, const uint8_t *file, size_t len, int16_t **out, size_t *n_interleaved, flo_info *info) {
+    if (!file) { set_err("bad argument"); return FLO_ERR_ARG; }
+    return decode_impl(c, file, nullptr, len, nullptr, 0, (void **)out, n_interleaved, info, 1);
+}
+extern "C" int flo_decode_i16_device(flo_ctx *c, const void *d_file, size_t len, int16_t *d_out, size_t d_out_capacity,
+                                     size_t *n_interleaved, flo_info *info) {
+    if (!d_file) { set_err("bad argument"); return FLO_ERR_ARG; }
+    return decode_impl(c, nullptr, d_file, len, d_out, d_out_capacity, nullptr, n_interleaved, info, 1);
 }

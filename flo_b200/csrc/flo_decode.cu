@@ -309,7 +309,7 @@ struct Lane {
     uint32_t rs;                      // this lane's ring column (shared-window address)
     uint32_t msa, msb, mshift;        // output = (s * msa + neighbour * msb) / 2^mshift, truncating (mid/side inverse)
     const uint8_t *pcm; uint32_t pcm_bytes;
-    float *outp; uint32_t stride;
+    uint8_t *outp; uint32_t stride;   // this lane's channel of the interleaved output (f32 or i16 elements), element stride
     uint32_t n, k;
     int src;                          // M_*
     int order, shift;                 // taps in use; >> shift (0 for the fixed predictors)
@@ -328,16 +328,24 @@ __device__ __forceinline__ int32_t next_residual(Lane &L, uint32_t i) {
 // `o` is the neighbour lane's sample (the other channel of a stereo frame): L = (m + s) / 2 on the even lane,
 // R = (m - s) / 2 on the odd one, `/` truncating toward zero, all in wrapping 32-bit arithmetic; other frames
 // pass s through.  One multiply-add form for all three so that the sample loop has no selects.
-__device__ __forceinline__ float to_output(const Lane &L, int32_t s, int32_t o) {
+// OUT = float: the reference's output.  OUT = int16_t: the same integer sample before i32_to_f32, saturated to 16 bits
+// (flo_decode_i16: half the bytes to store and to copy to the host).
+template <typename OUT>
+__device__ __forceinline__ OUT to_output(const Lane &L, int32_t s, int32_t o) {
     const uint32_t t = (uint32_t)s * L.msa + (uint32_t)o * L.msb;
     const int32_t v = (int32_t)(t + ((t >> 31) & L.mshift)) >> L.mshift;
-    return __fmul_rn(__int2float_rn(v), 1.0f / 32767.0f);
+    if constexpr (sizeof(OUT) == 2) return (OUT)max(-32768, min(32767, v));
+    else return __fmul_rn(__int2float_rn(v), 1.0f / 32767.0f);
 }
 __device__ __forceinline__ void store_if(float *p, float v, bool on) {     // predicated store: no branch in the sample loop
     asm volatile("{\n .reg .pred q;\n setp.ne.u32 q, %2, 0;\n @q st.global.f32 [%0], %1;\n}" :: "l"(p), "f"(v), "r"((uint32_t)on) : "memory");
 }
+__device__ __forceinline__ void store_if(int16_t *p, int16_t v, bool on) {
+    asm volatile("{\n .reg .pred q;\n setp.ne.u32 q, %2, 0;\n @q st.global.b16 [%0], %1;\n}" :: "l"(p), "h"(v), "r"((uint32_t)on) : "memory");
+}
+template <typename OUT>
 __device__ __forceinline__ void emit(const Lane &L, uint32_t i, int32_t s) {
-    store_if(L.outp + (size_t)i * L.stride, to_output(L, s, __shfl_xor_sync(FULL, s, 1)), i < L.n);
+    store_if(reinterpret_cast<OUT *>(L.outp) + (size_t)i * L.stride, to_output<OUT>(L, s, __shfl_xor_sync(FULL, s, 1)), i < L.n);
 }
 
 // ---- predictor side ----
@@ -356,19 +364,20 @@ __device__ __forceinline__ int32_t fir(const int32_t (&c)[ORD], const int32_t (&
 // Steady state (sample index >= 12 >= order): reconstruct_lpc_int's loop (decoder.rs:169-179) / the fixed
 // recurrences (decoder.rs:199-259) as one FIR of at most ORD taps.  Fully unrolled over the block, so the history
 // is renamed instead of moved and the shuffle / convert / store of sample t overlap the filter step of t + 1.
-template <int ORD>
-__device__ __forceinline__ void consume_block(const Lane &L, uint32_t res, uint32_t i0, const int32_t (&c)[ORD], int32_t (&h)[ORD], float *&op) {
+template <int ORD, typename OUT>
+__device__ __forceinline__ void consume_block(const Lane &L, uint32_t res, uint32_t i0, const int32_t (&c)[ORD], int32_t (&h)[ORD], OUT *&op) {
     #pragma unroll
     for (int t = 0; t < BLK; t++) {
         const int32_t s = fir<ORD>(c, h, L.shift, unzigzag(lds32(res + 128u * t)));
         #pragma unroll
         for (int j = ORD - 1; j > 0; j--) h[j] = h[j - 1];
         h[0] = s;
-        store_if(op, to_output(L, s, __shfl_xor_sync(FULL, s, 1)), i0 + t < L.n);
+        store_if(op, to_output<OUT>(L, s, __shfl_xor_sync(FULL, s, 1)), i0 + t < L.n);
         op += L.stride;
     }
 }
 // Generic step with the history newest-first in hist[]: warm-up rules (decoder.rs:163-165, 199-259).
+template <typename OUT>
 __device__ __forceinline__ void synth_apply(const Lane &L, uint32_t i, int32_t r, const int32_t (&c12)[12], int32_t (&hist)[12]) {
     int32_t pred = 0;
     if (i >= (uint32_t)L.order) {
@@ -386,23 +395,23 @@ __device__ __forceinline__ void synth_apply(const Lane &L, uint32_t i, int32_t r
     #pragma unroll
     for (int j = 11; j > 0; j--) hist[j] = hist[j - 1];
     hist[0] = s;
-    emit(L, i, s);
+    emit<OUT>(L, i, s);
 }
 // Predictor warp: block b of residuals is consumed while the bit-reading warp produces block b + 1.
-template <int ORD>
+template <int ORD, typename OUT>
 __device__ __forceinline__ void consumer_loop(const Lane &L, uint32_t res0, uint32_t nblk, const int32_t (&c12)[12], int32_t (&hist)[12]) {
     int32_t c[ORD], h[ORD];
     #pragma unroll
     for (int j = 0; j < ORD; j++) { c[j] = c12[j]; h[j] = 0; }
-    float *op = L.outp + (size_t)BLK * L.stride;
+    OUT *op = reinterpret_cast<OUT *>(L.outp) + (size_t)BLK * L.stride;
     for (uint32_t ph = 0; ph <= nblk; ph++) {
         if (ph == 1) {                                     // first block: warm-up rules, generic taps
             #pragma unroll 1
-            for (int t = 0; t < BLK; t++) synth_apply(L, (uint32_t)t, unzigzag(lds32(res0 + 128u * t)), c12, hist);
+            for (int t = 0; t < BLK; t++) synth_apply<OUT>(L, (uint32_t)t, unzigzag(lds32(res0 + 128u * t)), c12, hist);
             #pragma unroll
             for (int j = 0; j < ORD; j++) h[j] = hist[j];
         } else if (ph > 1) {
-            consume_block<ORD>(L, res0 + (((ph - 1) & 1u) ? 128u * BLK : 0u), (ph - 1) * BLK, c, h, op);
+            consume_block<ORD, OUT>(L, res0 + (((ph - 1) & 1u) ? 128u * BLK : 0u), (ph - 1) * BLK, c, h, op);
         }
         __syncthreads();
     }
@@ -455,7 +464,7 @@ __device__ __forceinline__ void lane_setup(const DecodeParams &p, unsigned long 
     const uint32_t C = p.channels;
     const uint8_t *f = p.file;
     L.n = 0; L.k = 0; L.src = M_ZERO; L.order = 0; L.shift = 0; L.fixed = false; L.ms = false; L.odd = (lane & 1u) != 0;
-    L.pcm = f; L.pcm_bytes = 0; L.outp = p.out; L.stride = C;
+    L.pcm = f; L.pcm_bytes = 0; L.outp = (uint8_t *)p.out; L.stride = C;
     #pragma unroll
     for (int j = 0; j < 12; j++) { c12[j] = 0; hist[j] = 0; }
     rpos = 0; rbytes = 0;
@@ -470,7 +479,7 @@ __device__ __forceinline__ void lane_setup(const DecodeParams &p, unsigned long 
         const uint32_t type = fr.type_flags & 0xFFu, flags = (fr.type_flags >> 8) & 0xFFu;
         L.n = fr.n;
         L.ms = C == 2 && (flags & 1u);
-        L.outp = p.out + (size_t)p.base[fi] * C + ch;
+        L.outp = (uint8_t *)p.out + ((size_t)p.base[fi] * C + ch) * (p.out_i16 ? 2u : 4u);
         const unsigned long long ch_end = un.pos + un.size;
         if (type == FT_RAW) {                              // reader.rs:182-188
             const unsigned long long need = 2ull * fr.n;
@@ -537,6 +546,7 @@ __device__ __forceinline__ void lane_setup(const DecodeParams &p, unsigned long 
 // One CTA = 32 units and two warps.  Rice decoding and the predictor are two serial chains per channel; run by one
 // warp they add up (and a lone warp has nobody to hide its stalls behind).  Warp 0 runs the bit reader, warp 1 the
 // predictor + mid/side + output, one block of BLK residuals apart, handing over through shared memory.
+template <typename OUT>
 __global__ void __launch_bounds__(64) k_dec_units(DecodeParams p) {
     __shared__ uint32_t ring[RING * 32];
     __shared__ uint32_t resbuf[2 * BLK * 32];
@@ -560,9 +570,9 @@ __global__ void __launch_bounds__(64) k_dec_units(DecodeParams p) {
         bits_init(L.rs, L.bits, p.file, p.len, L.src == M_RICE ? rpos : 0ull, L.src == M_RICE ? rbytes : 0u);
         producer_loop(L, res0, nblk, any_pcm);
     } else {
-        if (omax <= 4) consumer_loop<4>(L, res0, nblk, c12, hist);
-        else if (omax <= 8) consumer_loop<8>(L, res0, nblk, c12, hist);
-        else consumer_loop<12>(L, res0, nblk, c12, hist);
+        if (omax <= 4) consumer_loop<4, OUT>(L, res0, nblk, c12, hist);
+        else if (omax <= 8) consumer_loop<8, OUT>(L, res0, nblk, c12, hist);
+        else consumer_loop<12, OUT>(L, res0, nblk, c12, hist);
     }
 }
 
@@ -575,7 +585,10 @@ cudaError_t launch_decode_parse(const DecodeParams &p, cudaStream_t st) {
 }
 cudaError_t launch_decode_units(const DecodeParams &p, cudaStream_t st) {
     const unsigned long long units = (unsigned long long)p.n_toc * p.channels;
-    if (units) k_dec_units<<<(unsigned)((units + 31) / 32), 64, 0, st>>>(p);
+    if (units) {
+        if (p.out_i16) k_dec_units<int16_t><<<(unsigned)((units + 31) / 32), 64, 0, st>>>(p);
+        else k_dec_units<float><<<(unsigned)((units + 31) / 32), 64, 0, st>>>(p);
+    }
     return cudaGetLastError();
 }
 

@@ -164,7 +164,8 @@ struct DecodeParams {
     unsigned long long *base;         // [n_toc] exclusive prefix of frame_samples
     uint32_t *ctl;                    // [0] index of the first TOC entry the reader breaks on (init n_toc), [1] smallest error key
                                       // (init 0xFFFFFFFF; frame << 13 | (channel + 1) << 4 | DecErr), [2..3] total sample frames (u64)
-    float *out;                       // interleaved f32, total * channels
+    void *out;                        // interleaved samples, total * channels: f32, or i16 when out_i16
+    int out_i16;                      // 1: the integer samples before i32_to_f32, saturated to i16 (flo_decode_i16)
 };
 cudaError_t launch_decode_parse(const DecodeParams &p, cudaStream_t st);   // parse + scan (2 kernels)
 cudaError_t launch_decode_units(const DecodeParams &p, cudaStream_t st);   // 1 kernel

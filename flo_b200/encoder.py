@@ -144,6 +144,26 @@ class Context:
         weakref.finalize(raw, self._L.flo_free, C.c_void_p(out.value))
         return np.frombuffer(raw, dtype=np.float32), _info_dict(info)
 
+    def decode_i16(self, data) -> Tuple[np.ndarray, dict]:
+        """flo_decode_i16: the decoder's integer samples saturated to int16 (half the bytes of decode())."""
+        buf = np.frombuffer(data, dtype=np.uint8) if not isinstance(data, np.ndarray) else np.ascontiguousarray(data, dtype=np.uint8)
+        out, n, info = C.c_void_p(), C.c_size_t(), _lib.Info()
+        ptr = buf.ctypes.data if buf.size else C.addressof(C.create_string_buffer(1))
+        _lib.check(self._L.flo_decode_i16(self._h, C.c_void_p(ptr), buf.size, C.byref(out), C.byref(n), C.byref(info)))
+        if n.value == 0:
+            self._L.flo_free(out)
+            return np.zeros(0, dtype=np.int16), _info_dict(info)
+        raw = (C.c_int16 * n.value).from_address(out.value)
+        weakref.finalize(raw, self._L.flo_free, C.c_void_p(out.value))
+        return np.frombuffer(raw, dtype=np.int16), _info_dict(info)
+
+    def decode_i16_device(self, d_file: int, length: int, d_out: int, capacity: int) -> Tuple[int, dict]:
+        """Device-resident flo_decode_i16 (capacity in int16 samples)."""
+        n, info = C.c_size_t(), _lib.Info()
+        _lib.check(self._L.flo_decode_i16_device(self._h, C.c_void_p(int(d_file)), int(length), C.c_void_p(int(d_out) or None),
+                                                 int(capacity), C.byref(n), C.byref(info)))
+        return int(n.value), _info_dict(info)
+
     def decode_device(self, d_file: int, length: int, d_out: int, capacity: int) -> Tuple[int, dict]:
         """Device-resident decode: `d_file` / `d_out` are device pointers (capacity in floats).
         Returns (interleaved sample count, info)."""
@@ -302,6 +322,10 @@ class Decoder:
     def decode(self, data) -> np.ndarray:
         """Decoder::decode(&self, data: &[u8]) -> FloResult<Vec<f32>>: interleaved f32 samples."""
         return self._context().decode(data)[0]
+
+    def decode_i16(self, data) -> np.ndarray:
+        """The same samples as 16-bit integers (before the reference's final i32 -> f32 conversion, saturated)."""
+        return self._context().decode_i16(data)[0]
 
     def decode_with_info(self, data) -> Tuple[np.ndarray, dict]:
         return self._context().decode(data)

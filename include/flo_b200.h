@@ -172,6 +172,14 @@ int flo_decode(flo_ctx *ctx, const uint8_t *file, size_t len, float **out, size_
 int flo_decode_device(flo_ctx *ctx, const void *d_file, size_t len, float *d_out, size_t d_out_capacity,
                       size_t *n_interleaved, flo_info *info);
 
+/* The same decode with 16-bit output: the integer samples Decoder::decode holds before its final i32 -> f32
+ * conversion (lossless/decoder.rs:61-72: `sample as f32 / 32767.0`), saturated to i16 -- for callers that feed a
+ * 16-bit sink (WAV writer, sound device): half the bytes leave the device.  Same errors, same info; capacity and
+ * *n_interleaved count samples.  flo_decode's f32 result equals (float)i16 * (1/32767) wherever |sample| <= 32767. */
+int flo_decode_i16(flo_ctx *ctx, const uint8_t *file, size_t len, int16_t **out, size_t *n_interleaved, flo_info *info);
+int flo_decode_i16_device(flo_ctx *ctx, const void *d_file, size_t len, int16_t *d_out, size_t d_out_capacity,
+                          size_t *n_interleaved, flo_info *info);
+
 /* -------------------------------------------------------------------------
  * Waveform peaks of the analysis metadata libflo::encode() attaches.  Replaces
  *   core::analysis::extract_waveform_peaks(samples, channels, sample_rate, peaks_per_second) -> WaveformData

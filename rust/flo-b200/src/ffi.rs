@@ -83,6 +83,10 @@ extern "C" {
                       info: *mut flo_info) -> c_int;
     pub fn flo_decode_device(ctx: *mut flo_ctx, d_file: *const c_void, len: usize, d_out: *mut f32,
                              d_out_capacity: usize, n_interleaved: *mut usize, info: *mut flo_info) -> c_int;
+    pub fn flo_decode_i16(ctx: *mut flo_ctx, file: *const u8, len: usize, out: *mut *mut i16, n_interleaved: *mut usize,
+                          info: *mut flo_info) -> c_int;
+    pub fn flo_decode_i16_device(ctx: *mut flo_ctx, d_file: *const c_void, len: usize, d_out: *mut i16,
+                                 d_out_capacity: usize, n_interleaved: *mut usize, info: *mut flo_info) -> c_int;
     pub fn flo_output_bound(tracks: *const flo_track, n_tracks: usize) -> usize;
     pub fn flo_ctx_set_stream(ctx: *mut flo_ctx, cuda_stream: *mut c_void) -> c_int;
     pub fn flo_ctx_last_timing(ctx: *mut flo_ctx, ms: *mut f32, launches: *mut u32) -> c_int;

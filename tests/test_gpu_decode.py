@@ -315,3 +315,34 @@ def test_decode_on_caller_stream_and_concurrent_contexts(fb):
     for c in ctxs:
         c.close()
     assert not errs, errs
+
+
+def test_i16_output_entry(fb):
+    """flo_decode_i16: the integer samples before i32_to_f32 (decoder.rs:61-72), saturated to i16 -- against the oracle's
+    integer decode; and its relation to the f32 entry."""
+    import torch
+    for sr, ch, level, n in ((44100, 2, 5, 3 * 44100 + 17), (8000, 1, 9, 20001), (48000, 6, 3, 30000), (44100, 2, 0, 50000)):
+        pcm = synth_pcm16(n, ch, sr, seed=0xD16 + ch + level, kind="multitone", noise_lsb=64)
+        img = fb.Encoder(sr, ch, 16).with_compression(level).encode_pcm16(pcm, b"")
+        want = np.clip(oracle.decode_i32(img), -32768, 32767).astype(np.int16)
+        got = fb.Decoder().decode_i16(img)
+        assert got.dtype == np.int16 and np.array_equal(got, want)
+        f32 = fb.Decoder().decode(img)
+        ok = np.abs(want.astype(np.int32)) <= 32767
+        assert np.array_equal(f32[ok], (want[ok].astype(np.float32) * np.float32(1.0 / 32767.0)))
+    # saturation: a hand-built file whose samples leave the 16-bit range
+    big = rice_channel(np.array([40000, -40000, 123, -32768, 32767, 70000], np.int64), 12, shift=128)
+    data = build_file(1, [(1, 6, 0, [big])])
+    assert fb.Decoder().decode_i16(data).tolist() == [32767, -32768, 123, -32768, 32767, 32767]
+    # device-resident entry and the capacity error
+    ctx = fb.default_context(0)
+    dev = torch.device("cuda", 0)
+    d_file = torch.from_numpy(np.frombuffer(img, np.uint8).copy()).to(dev)
+    d_out = torch.empty(want.size, dtype=torch.int16, device=dev)
+    n_dec, info = ctx.decode_i16_device(d_file.data_ptr(), len(img), d_out.data_ptr(), d_out.numel())
+    assert n_dec == want.size and np.array_equal(d_out.cpu().numpy(), want) and info["channels"] == 2
+    with pytest.raises(fb.FloError):
+        ctx.decode_i16_device(d_file.data_ptr(), len(img), d_out.data_ptr(), want.size - 1)
+    with pytest.raises(fb.FloError) as e:
+        fb.Decoder().decode_i16(img[: len(img) - 40])
+    assert str(e.value) == "Unexpected end of file"

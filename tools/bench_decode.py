@@ -55,5 +55,13 @@ for it in range(4):
     lt = ctx.last_timing()
     del out
 res["host_entry_pinned_ms"] = min(he[1:])
+he = []
+for it in range(4):                                                  # flo_decode_i16: half the bytes come back
+    t0 = time.perf_counter()
+    out, info = ctx.decode_i16(pinned)
+    he.append((time.perf_counter() - t0) * 1e3)
+    lt16 = ctx.last_timing()
+    del out
+res["host_entry_pinned_i16_ms"] = min(he[1:]); res["i16_units_kernel_ms"] = lt16["encode_ms"]; res["i16_d2h_ms"] = lt16["d2h_ms"]
 res["host_pinned_h2d_ms"] = lt["h2d_ms"]
 print(json.dumps(res))
