@@ -112,7 +112,7 @@ struct BitIn {
     uint32_t npend;
     uint32_t wr, rd;                  // ring word counters: next word to store / word held in nxt
     unsigned long long end_off;       // payload end, as a byte offset from the aligned base of the stream
-    uint32_t nxt;                     // ring[rd] as stored (little-endian), loaded ahead; byte-swapped when appended
+    uint32_t nxt;                     // ring[rd] (big-endian, ready to append), loaded ahead
     unsigned long long buf;           // MSB-aligned window
     int nb;                           // bits in the window
 };
@@ -120,11 +120,13 @@ struct BitIn {
 __device__ __forceinline__ uint32_t lds32(uint32_t a) { uint32_t v; asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(a) : "memory"); return v; }
 __device__ __forceinline__ void sts32(uint32_t a, uint32_t v) { asm volatile("st.shared.u32 [%0], %1;" :: "r"(a), "r"(v) : "memory"); }
 __device__ __forceinline__ uint32_t ring_at(uint32_t rs, uint32_t idx) { return lds32(rs + ((idx & (RING - 1)) << 7)); }
-__device__ __forceinline__ uint32_t be(uint32_t raw) { return __byte_perm(raw, 0u, 0x0123); }
+// The ring holds big-endian words: the swap happens where a word is stored (once per word, a volatile PRMT right in front of
+// the volatile store, so it cannot be hoisted up to the load), not on the per-code path of the reader.
+__device__ __forceinline__ uint32_t be_store(uint32_t raw) { uint32_t v; asm volatile("prmt.b32 %0, %1, 0, 0x0123;" : "=r"(v) : "r"(raw)); return v; }
 // Past the end of the image the address is clamped (the bytes are masked off in put_vec anyway): nothing may
 // depend on the loaded registers until the next top-up stores them.
 __device__ __forceinline__ uint4 ldv(const uint4 *p, const uint4 *end) { return __ldg(p < end ? p : end - 1); }
-// Words go into the ring as loaded (little-endian); the pop side byte-swaps.  Nothing here may touch the loaded
+// Words go into the ring byte-swapped (big-endian), by a volatile PRMT directly in front of the store.  Nothing else here may touch the loaded
 // registers except the stores themselves, or the compiler hoists that work to right behind the loads and the
 // warp waits out the full memory latency at every top-up.
 __device__ __forceinline__ uint32_t le_masked(uint32_t raw, unsigned long long pos, unsigned long long end_off) {
@@ -135,10 +137,10 @@ __device__ __forceinline__ void put_vec(uint32_t rs, BitIn &b, const uint4 &v) {
     const uint32_t slot = rs + ((b.wr & (RING - 1)) << 7);  // wr is a multiple of 4: the four slots do not wrap
     const unsigned long long pos = 4ull * b.wr;
     if (pos + 16 <= b.end_off) {
-        sts32(slot, v.x); sts32(slot + 128, v.y); sts32(slot + 256, v.z); sts32(slot + 384, v.w);
+        sts32(slot, be_store(v.x)); sts32(slot + 128, be_store(v.y)); sts32(slot + 256, be_store(v.z)); sts32(slot + 384, be_store(v.w));
     } else {                                               // the payload ends inside this vector: later bytes read as 0
-        sts32(slot, le_masked(v.x, pos, b.end_off)); sts32(slot + 128, le_masked(v.y, pos + 4, b.end_off));
-        sts32(slot + 256, le_masked(v.z, pos + 8, b.end_off)); sts32(slot + 384, le_masked(v.w, pos + 12, b.end_off));
+        sts32(slot, be_store(le_masked(v.x, pos, b.end_off))); sts32(slot + 128, be_store(le_masked(v.y, pos + 4, b.end_off)));
+        sts32(slot + 256, be_store(le_masked(v.z, pos + 8, b.end_off))); sts32(slot + 384, be_store(le_masked(v.w, pos + 12, b.end_off)));
     }
     b.wr += 4;
 }
@@ -174,7 +176,7 @@ __device__ __forceinline__ void bits_init(uint32_t rs, BitIn &b, const uint8_t *
     topup(rs, b);
     b.rd = sk >> 2;                                        // the payload starts sk bytes into the first vector
     const uint32_t sb = sk & 3u;
-    const uint32_t w = be(ring_at(rs, b.rd));
+    const uint32_t w = ring_at(rs, b.rd);
     b.rd++;
     b.buf = sb ? (unsigned long long)(w << (8u * sb)) << 32 : (unsigned long long)w << 32;
     b.nb = 32 - 8 * (int)sb;
@@ -189,7 +191,7 @@ __device__ __forceinline__ void lane_fill(uint32_t rs, BitIn &b, int want) {
 }
 __device__ __forceinline__ void refill_slow(uint32_t rs, BitIn &b) {
     if (b.nb > 32) return;
-    b.buf |= (unsigned long long)be(b.nxt) << (32 - b.nb); b.nb += 32; b.rd++;
+    b.buf |= (unsigned long long)b.nxt << (32 - b.nb); b.nb += 32; b.rd++;
     b.nxt = ring_at(rs, b.rd);
 }
 // decode_i32's loop body (rice.rs:127-155): unary quotient (ones, capped at 256 reads), k-bit remainder, zigzag.
@@ -224,7 +226,7 @@ __device__ __forceinline__ uint32_t rice_slow(uint32_t rs, BitIn &b, uint32_t k)
 __device__ __forceinline__ uint32_t rice_try(uint32_t rs, BitIn &b, uint32_t k, bool &ok) {
     uint32_t hi = (uint32_t)(b.buf >> 32), lo = (uint32_t)b.buf;
     if (b.nb <= 32) {                                      // the low word of the window is empty
-        const uint32_t w = be(b.nxt);
+        const uint32_t w = b.nxt;
         hi |= __funnelshift_rc(w, 0u, (uint32_t)b.nb);
         lo = __funnelshift_lc(0u, w, 32u - (uint32_t)b.nb);
         b.nb += 32;
@@ -252,7 +254,7 @@ struct RiceK { uint32_t k, kp1, lim, pk; };               // k, k + 1, 31 - k, 2
 __device__ __forceinline__ uint32_t rice_step(uint32_t rs, uint32_t &hi, uint32_t &lo, int &nb, uint32_t &rd, uint32_t &nxt,
                                               const RiceK &K, bool &all_ok) {
     if (nb <= 32) {
-        const uint32_t w = be(nxt);
+        const uint32_t w = nxt;
         hi |= __funnelshift_rc(w, 0u, (uint32_t)nb);
         lo = __funnelshift_lc(0u, w, 32u - (uint32_t)nb);
         nb += 32;
