@@ -253,10 +253,12 @@ __device__ __forceinline__ uint32_t rice_try(uint32_t rs, BitIn &b, uint32_t k, 
 struct RiceK { uint32_t k, kp1, lim, pk; };               // k, k + 1, 31 - k, 2^k
 __device__ __forceinline__ uint32_t rice_step(uint32_t rs, uint32_t &hi, uint32_t &lo, int &nb, uint32_t &rd, uint32_t &nxt,
                                               const RiceK &K, bool &all_ok) {
-    if (nb <= 32) {                                        // (w : 0) >> nb: upper word into hi, lower word is the new lo
-        const uint32_t w = nxt;
-        hi |= __funnelshift_rc(w, 0u, (uint32_t)nb);
-        lo = __funnelshift_rc(0u, w, (uint32_t)nb);
+    // Append the look-ahead word when the low word of the window is empty: (w : 0) >> nb, upper word into hi, lower word is
+    // the new lo.  The shift clamps at 32, so with more than 32 bits on hand the upper word is 0 and hi takes it
+    // unconditionally -- the compare is off the chain that leads to the next leading-ones count.
+    hi |= __funnelshift_rc(nxt, 0u, (uint32_t)nb);
+    if (nb <= 32) {
+        lo = __funnelshift_rc(0u, nxt, (uint32_t)nb);
         nb += 32;
         rd++;
     }
