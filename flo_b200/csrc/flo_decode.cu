@@ -103,7 +103,7 @@ __global__ void __launch_bounds__(1024) k_dec_scan(DecodeParams p) {
 // streams are staged through shared memory instead: a 32-word ring per lane (word-interleaved, bank = lane),
 // topped up at warp-uniform points with 16-byte loads that are stored to the ring one top-up later.  The
 // per-sample path is branch-free: one predicated 32-bit append and one unconditional LDS of the next word.
-constexpr int RING = 64;              // words per lane
+constexpr int RING = 128;             // words per lane
 constexpr int GROUP = 16;             // samples between top-ups (long enough for the loads of one top-up to land before the
                                       // next stores them); the fast path pops at most one word per sample
 struct BitIn {
@@ -159,10 +159,11 @@ __device__ __forceinline__ void topup_once(uint32_t rs, BitIn &b) {
     if (room >= 12) { b.p2 = ldv(b.gp, b.vend); b.gp++; b.npend = 3; }
     if (room >= 16) { b.p3 = ldv(b.gp, b.vend); b.gp++; b.npend = 4; }
 }
-// Warp-uniform.  Afterwards every lane holds at least 2 * GROUP words, so the fast path cannot run dry before the next call.
+// Warp-uniform, once per TWO groups.  Afterwards every lane holds at least 4 * GROUP words, so the fast path (at most one word
+// per code) cannot run dry before the next call.
 __device__ __forceinline__ void topup(uint32_t rs, BitIn &b) {
     do topup_once(rs, b);
-    while (__any_sync(FULL, b.wr - b.rd < 2 * GROUP));      // rare second trip: waits for the loads just issued
+    while (__any_sync(FULL, b.wr - b.rd < 4 * GROUP));      // further trips (high bit rates): wait for the loads just issued
 }
 __device__ __forceinline__ void bits_init(uint32_t rs, BitIn &b, const uint8_t *file, unsigned long long len,
                                           unsigned long long start, uint32_t nbytes) {
@@ -198,7 +199,7 @@ __device__ __forceinline__ void refill_slow(uint32_t rs, BitIn &b) {
 // Rare path: the code does not fit the bits on hand (long unary run, large k).  One code takes at most
 // 256 + 1 + 31 bits = 9 words; with 20 on hand at entry the rest of the group still pops without checking.
 __device__ __forceinline__ uint32_t rice_slow(uint32_t rs, BitIn &b, uint32_t k) {
-    lane_fill(rs, b, GROUP + 12);
+    lane_fill(rs, b, 2 * GROUP + 12);                     // this code and what is left of the two groups between top-ups
     b.nxt = ring_at(rs, b.rd);
     uint32_t q = 0;
     for (;;) {
@@ -428,7 +429,7 @@ __device__ __forceinline__ void producer_loop(Lane &L, uint32_t res0, uint32_t n
             const uint32_t res = res0 + ((ph & 1u) ? 128u * BLK : 0u);
             #pragma unroll 1
             for (int g = 0; g < BLK; g += GROUP) {
-                topup(L.rs, L.bits);
+                if ((ph & 1u) == 0) topup(L.rs, L.bits);           // every other group: half the top-up instructions per code
                 if (!any_pcm) {
                     // The whole group as one transaction: GROUP codes straight-line with predication only; if any of
                     // them did not fit the bits on hand, roll the reader back and redo the group code by code.
