@@ -348,6 +348,18 @@ __device__ __forceinline__ void store_if(float *p, float v, bool on) {     // pr
 __device__ __forceinline__ void store_if(int16_t *p, int16_t v, bool on) {
     asm volatile("{\n .reg .pred q;\n setp.ne.u32 q, %2, 0;\n @q st.global.b16 [%0], %1;\n}" :: "l"(p), "h"(v), "r"((uint32_t)on) : "memory");
 }
+// Store v at p + T * step bytes if T < rem: the compare lives inside the asm (one SETP, no boolean materialised), the
+// address is one multiply-add from the block's base.
+template <int T>
+__device__ __forceinline__ void store_lt(uint8_t *base, uint32_t step_bytes, float v, uint32_t rem) {
+    float *p = reinterpret_cast<float *>(base + (size_t)T * step_bytes);
+    asm volatile("{\n .reg .pred q;\n setp.gt.u32 q, %2, %3;\n @q st.global.f32 [%0], %1;\n}" :: "l"(p), "f"(v), "r"(rem), "n"(T) : "memory");
+}
+template <int T>
+__device__ __forceinline__ void store_lt(uint8_t *base, uint32_t step_bytes, int16_t v, uint32_t rem) {
+    int16_t *p = reinterpret_cast<int16_t *>(base + (size_t)T * step_bytes);
+    asm volatile("{\n .reg .pred q;\n setp.gt.u32 q, %2, %3;\n @q st.global.b16 [%0], %1;\n}" :: "l"(p), "h"(v), "r"(rem), "n"(T) : "memory");
+}
 template <typename OUT>
 __device__ __forceinline__ void emit(const Lane &L, uint32_t i, int32_t s) {
     store_if(reinterpret_cast<OUT *>(L.outp) + (size_t)i * L.stride, to_output<OUT>(L, s, __shfl_xor_sync(FULL, s, 1)), i < L.n);
@@ -369,17 +381,20 @@ __device__ __forceinline__ int32_t fir(const int32_t (&c)[ORD], const int32_t (&
 // Steady state (sample index >= 12 >= order): reconstruct_lpc_int's loop (decoder.rs:169-179) / the fixed
 // recurrences (decoder.rs:199-259) as one FIR of at most ORD taps.  Fully unrolled over the block, so the history
 // is renamed instead of moved and the shuffle / convert / store of sample t overlap the filter step of t + 1.
+template <int ORD, typename OUT, int T>
+__device__ __forceinline__ void consume_one(const Lane &L, uint32_t res, const int32_t (&c)[ORD], int32_t (&h)[ORD], uint8_t *base, uint32_t step_bytes, uint32_t rem) {
+    const int32_t s = fir<ORD>(c, h, L.shift, unzigzag(lds32(res + 128u * T)));
+    #pragma unroll
+    for (int j = ORD - 1; j > 0; j--) h[j] = h[j - 1];
+    h[0] = s;
+    store_lt<T>(base, step_bytes, to_output<OUT>(L, s, __shfl_xor_sync(FULL, s, 1)), rem);
+    if constexpr (T + 1 < BLK) consume_one<ORD, OUT, T + 1>(L, res, c, h, base, step_bytes, rem);
+}
 template <int ORD, typename OUT>
 __device__ __forceinline__ void consume_block(const Lane &L, uint32_t res, uint32_t i0, const int32_t (&c)[ORD], int32_t (&h)[ORD], OUT *&op) {
-    #pragma unroll
-    for (int t = 0; t < BLK; t++) {
-        const int32_t s = fir<ORD>(c, h, L.shift, unzigzag(lds32(res + 128u * t)));
-        #pragma unroll
-        for (int j = ORD - 1; j > 0; j--) h[j] = h[j - 1];
-        h[0] = s;
-        store_if(op, to_output<OUT>(L, s, __shfl_xor_sync(FULL, s, 1)), i0 + t < L.n);
-        op += L.stride;
-    }
+    const uint32_t rem = L.n > i0 ? L.n - i0 : 0u, step_bytes = L.stride * (uint32_t)sizeof(OUT);
+    consume_one<ORD, OUT, 0>(L, res, c, h, reinterpret_cast<uint8_t *>(op), step_bytes, rem);
+    op += (size_t)BLK * L.stride;
 }
 // Generic step with the history newest-first in hist[]: warm-up rules (decoder.rs:163-165, 199-259).
 template <typename OUT>
