@@ -79,21 +79,21 @@ class Context:
         n = len(tracks)
         if n == 0:
             return []
-        arr = (_lib.Track * n)()
-        keep = []
         dt = {FMT_F32: np.float32, FMT_PCM16: np.int16, FMT_U8: np.uint8, FMT_S32: np.int32}[fmt]
-        for i, t in enumerate(tracks):
-            s = np.ascontiguousarray(t.samples, dtype=dt).reshape(-1)
-            m = bytes(t.metadata or b"")
-            mb = C.create_string_buffer(m, len(m)) if m else None
-            keep.append((s, mb))
-            arr[i].samples = s.ctypes.data if s.size else None
-            arr[i].n_interleaved = s.size
-            arr[i].sample_rate = _u(t.sample_rate, 32, "sample_rate")
-            arr[i].channels = _u(t.channels, 8, "channels")
-            arr[i].bit_depth = _u(t.bit_depth, 8, "bit_depth")
-            arr[i].meta = C.addressof(mb) if mb is not None else None
-            arr[i].meta_len = len(m)
+        # the flo_track table is filled column by column (a batch can hold thousands of tracks)
+        ss = [np.ascontiguousarray(t.samples, dtype=dt).reshape(-1) for t in tracks]
+        metas = [bytes(t.metadata) if t.metadata else b"" for t in tracks]
+        mbufs = [C.create_string_buffer(m, len(m)) if m else None for m in metas]
+        keep = (ss, mbufs)
+        rec = np.zeros(n, dtype=_TRACK_DT)
+        rec["samples"] = [s.__array_interface__["data"][0] if s.size else 0 for s in ss]
+        rec["n_interleaved"] = [s.size for s in ss]
+        rec["sample_rate"] = [_u(t.sample_rate, 32, "sample_rate") for t in tracks]
+        rec["channels"] = [_u(t.channels, 8, "channels") for t in tracks]
+        rec["bit_depth"] = [_u(t.bit_depth, 8, "bit_depth") for t in tracks]
+        rec["meta"] = [C.addressof(b) if b is not None else 0 for b in mbufs]
+        rec["meta_len"] = [len(m) for m in metas]
+        arr = (_lib.Track * n).from_buffer(rec)
         outs = (_lib.Out * n)()
         _lib.check(self._L.flo_encode_batch(self._h, arr, n, fmt, min(int(level), 255), outs))
         if views:
@@ -194,29 +194,47 @@ def _info_dict(info) -> dict:
     return {k: int(getattr(info, k)) for k, _ in _lib.Info._fields_}
 
 
+# numpy view of flo_track (include/flo_b200.h): the same offsets as the ctypes structure
+_TRACK_DT = np.dtype({"names": [f[0] for f in _lib.Track._fields_],
+                      "formats": [np.uint64, np.uint64, np.uint32, np.uint8, np.uint8, np.uint64, np.uint64],
+                      "offsets": [getattr(_lib.Track, f[0]).offset for f in _lib.Track._fields_],
+                      "itemsize": C.sizeof(_lib.Track)})
+
+
 class BatchResult:
-    """Zero-copy views of the file images returned by flo_encode_batch; close() hands them back (flo_free)."""
+    """Zero-copy views of the file images returned by flo_encode_batch; close() hands them back (flo_free).
+    The views are made on first access (a batch of thousands of tracks should not pay for arrays nobody reads)."""
 
     def __init__(self, L, outs):
         self._L, self._outs = L, outs
-        self.arrays = [np.ctypeslib.as_array(C.cast(o.data, C.POINTER(C.c_uint8)), shape=(o.len,)) if o.len
-                       else np.zeros(0, np.uint8) for o in outs]
+        self._arrays = None
+        # (data, len) pairs as one uint64 table over the ctypes array
+        self._table = np.frombuffer(outs, dtype=np.uint64).reshape(-1, 2) if len(outs) else np.zeros((0, 2), np.uint64)
+
+    @property
+    def arrays(self):
+        if self._arrays is None:
+            self._arrays = [np.ctypeslib.as_array(C.cast(o.data, C.POINTER(C.c_uint8)), shape=(o.len,)) if o.len
+                            else np.zeros(0, np.uint8) for o in (self._outs or [])]
+        return self._arrays
 
     def __len__(self):
-        return len(self.arrays)
+        return int(self._table.shape[0])
 
     def __getitem__(self, i):
         return self.arrays[i]
 
     def total_bytes(self) -> int:
-        return int(sum(a.size for a in self.arrays))
+        return int(self._table[:, 1].sum())
 
     def close(self) -> None:
         if self._outs is not None:
-            self.arrays = []
-            for o in self._outs:
-                self._L.flo_free(o.data)
+            self._arrays = []
+            free = self._L.flo_free
+            for ptr in self._table[:, 0].tolist():
+                free(ptr)
             self._outs = None
+            self._table = np.zeros((0, 2), np.uint64)
 
     def __enter__(self):
         return self
